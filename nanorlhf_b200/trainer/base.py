@@ -1,0 +1,500 @@
+"""The shared online-RL training loop.
+
+The reference ships seven near-identical copies of this loop, one per algorithm
+(/root/reference/GRPO/grpo_trainer.py:176-778 and siblings), each subclassing HF ``Trainer``.
+Here there is one ``RLTrainer`` that owns the six phases of an update:
+
+  1. tier optimizer state out of the way (optional)        -- runtime/offload.py   (K-OFF)
+  2. rollout with the in-process sampler                   -- sampler/engine.py    (K1-K5, K-BC)
+  3. reward callback ``reward_func(list[str], eos_token)``  -- reward/*
+  4. no-grad log-prob (/value) pass, policy + ref          -- models/qwen2.py      (K9, K-LP)
+  5. per-token rewards + advantage estimation              -- ops (K-GAE)
+  6. optimisation: epochs x mini-batches x micro-batches   -- ops (K-LOSS), parallel/optimizer.py (K-AR)
+
+and thin subclasses that override only the algorithm-specific hooks (``select_samples``,
+``token_rewards``, ``advantages``, ``micro_loss``).  Public surface matches the reference
+(SURVEY.md App. D): ``XTrainer(config, processing_class, policy, ref_policy, train_dataset,
+reward_func=..., callbacks=..., [value_model])``, ``.train()``, ``.save_model()``,
+``._save_checkpoint()``, ``.state / .control / .callback_handler``.
+"""
+from __future__ import annotations
+
+import math
+import os
+import random
+import time
+from collections import defaultdict
+from typing import Callable, Dict, List, Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import ops
+from ..config import RLConfig
+from ..models.qwen2 import response_logprobs
+from ..parallel.comm import Comm
+from ..parallel.optimizer import FusedAdamW, build_param_groups
+from ..runtime import checkpoint as ckpt
+from ..runtime.offload import TieringEngine
+from ..sampler import engine as sampler_engine
+from ..utils import (INVALID_LOGPROB, disable_dropout_in_model, exact_div, masked_whiten, response_masks,
+                     scatter_terminal_reward, truncate_response)
+from ..utils.batching import create_batches
+from ..utils.callbacks import (DEFAULT_CALLBACKS, CallbackHandler, OnlineTrainerState, ProgressCallback,
+                               TrainerControl)
+from ..utils.data import DataCollatorWithPadding, PromptLoader
+from ..utils.faults import Heartbeat, maybe_inject
+from ..utils.metrics import print_rich_table, reporting_callbacks
+from ..utils.profiling import PhaseTimer, check_finite
+from ..utils.schedules import get_scheduler
+
+
+class PolicyAndValueWrapper(nn.Module):
+    """Groups everything trainable (reference: grpo_trainer.py:82-88, ppo_trainer.py:87-99)."""
+
+    def __init__(self, policy, value_model=None):
+        super().__init__()
+        self.policy = policy
+        self.value_model = value_model
+
+    def forward(self, *a, **kw):
+        return self.policy(*a, **kw)
+
+
+class RLTrainer:
+    algo_name = "rl"
+    samples_per_prompt_field: Optional[str] = None    # e.g. "grpo_sample_N"
+    uses_value_model = False
+    kl_in_reward = True                               # every algorithm except GRPO
+    logs_policy_ratio_stats = True                    # RAFT drops approxkl/clipfrac/ratio
+
+    # ------------------------------------------------------------------------------------------
+    def __init__(self, config: RLConfig, processing_class, policy, ref_policy, train_dataset,
+                 value_model=None, data_collator=None, eval_dataset=None, optimizers=(None, None),
+                 callbacks=None, reward_func: Optional[Callable] = None, comm: Optional[Comm] = None,
+                 device=None, accuracy_func: Optional[Callable] = None):
+        if ref_policy is policy:
+            raise ValueError("`policy` and `ref_policy` cannot be the same object; pass a copy")
+        if reward_func is None:
+            raise ValueError("reward_func is required")
+        self.args = args = config
+        self.processing_class = self.tokenizer = processing_class
+        self.policy, self.ref_policy, self.value_model = policy, ref_policy, value_model
+        self.reward_func, self.accuracy_func = reward_func, accuracy_func
+        self.train_dataset, self.eval_dataset = train_dataset, eval_dataset
+        self.train_dataset_len = len(train_dataset)
+        self.data_collator = data_collator or DataCollatorWithPadding(processing_class)
+
+        self.comm = comm or Comm.from_env(device)
+        self.device = self.comm.device
+        self._derive_batch_sizes()
+
+        # run name with a timestamp agreed across ranks (reference broadcasts it: :241-243)
+        stamp = self.comm.broadcast_object(int(time.time()), 0)
+        args.run_name = args.run_name or f"{args.exp_name}__{args.seed}__{stamp}"
+        self.local_seed = args.seed + self.comm.rank * 100003      # per-rank seed (:244)
+        if args.stop_token == "eos":
+            args.stop_token_id = processing_class.eos_token_id
+
+        for m in (policy, ref_policy, value_model):
+            if m is not None:
+                disable_dropout_in_model(m)
+        self.model = PolicyAndValueWrapper(policy, value_model if self.uses_value_model else None)
+        self.model.to(self.device)
+        ref_policy.eval()
+        for p in ref_policy.parameters():
+            p.requires_grad_(False)
+        self.tiering = TieringEngine(self.device)
+        self.tiering.register("ref", ref_policy, args.role_residency("ref"))
+        if args.gradient_checkpointing:
+            policy.gradient_checkpointing_enable(args.gradient_checkpointing_kwargs)
+            if self.model.value_model is not None:
+                self.model.value_model.gradient_checkpointing_enable(args.gradient_checkpointing_kwargs)
+
+        self.optimizer, self.lr_scheduler = optimizers
+        if self.optimizer is None:
+            self.optimizer = self.create_optimizer()
+        if self.lr_scheduler is None:
+            self.lr_scheduler = get_scheduler(args.lr_scheduler_type, self.optimizer, args.warmup_steps,
+                                              args.num_total_batches, args.lr_scheduler_kwargs)
+        self.tiering.register_optimizer("optimizer", self.optimizer, args.role_residency("optimizer"))
+
+        self.state = OnlineTrainerState(is_local_process_zero=self.comm.local_rank == 0,
+                                        is_world_process_zero=self.comm.is_main)
+        self.control = TrainerControl()
+        cbs = [c() if isinstance(c, type) else c for c in DEFAULT_CALLBACKS]
+        cbs += [ProgressCallback()] + reporting_callbacks(args, args.run_name) + list(callbacks or [])
+        self.callback_handler = CallbackHandler(cbs, self.model, processing_class, self.optimizer, self.lr_scheduler)
+        self.state.stateful_callbacks = {type(c).__name__: c.state() for c in cbs if hasattr(c, "state")}
+
+        torch.manual_seed(args.seed)       # same shuffle on every rank, then shard
+        self.dataloader = PromptLoader(train_dataset, args.local_batch_size, self.data_collator, seed=args.seed,
+                                       rank=self.comm.rank, world_size=self.comm.world_size,
+                                       drop_last=args.dataloader_drop_last)
+        torch.manual_seed(self.local_seed)
+        self._np_rng = np.random.RandomState(self.local_seed % (2 ** 31))
+        self._select_gen = torch.Generator().manual_seed(self.local_seed)
+        self.timer = PhaseTimer(self.device, nvtx=args.profile == "nvtx")
+        self.heartbeat = Heartbeat(os.path.join(args.output_dir, "heartbeat"), self.comm.rank,
+                                   args.watchdog_timeout_s, enable_watchdog=self.comm.world_size > 1)
+        self.last_completions = None
+        self._resumed = False
+        if self.comm.is_main:
+            os.makedirs(args.output_dir, exist_ok=True)
+
+    # ---- batch arithmetic (grpo_trainer.py:220-240) --------------------------------------------
+    def _derive_batch_sizes(self):
+        a = self.args
+        a.world_size = self.comm.world_size
+        a.local_batch_size = a.per_device_train_batch_size * a.gradient_accumulation_steps * a.num_mini_batches
+        a.micro_batch_size = a.per_device_train_batch_size * a.world_size
+        a.batch_size = a.local_batch_size * a.world_size
+        a.mini_batch_size = exact_div(a.batch_size, a.num_mini_batches,
+                                      "`batch_size` must be a multiple of `num_mini_batches`")
+        a.local_mini_batch_size = exact_div(a.local_batch_size, a.num_mini_batches,
+                                            "`local_batch_size` must be a multiple of `num_mini_batches`")
+        a.num_total_batches = math.ceil(a.total_episodes / a.batch_size)
+
+    @property
+    def samples_per_prompt(self) -> int:
+        return int(getattr(self.args, self.samples_per_prompt_field)) if self.samples_per_prompt_field else 1
+
+    # ---- optimizer -----------------------------------------------------------------------------
+    def create_optimizer(self):
+        a = self.args
+        groups = build_param_groups(self.model.named_parameters(), a.weight_decay, a.learning_rate)
+        return self._make_optimizer(groups)
+
+    def _make_optimizer(self, groups):
+        a = self.args
+        sd = torch.bfloat16 if a.optimizer_state_dtype == "bf16" else torch.float32
+        mode = a.comm if self.device.type == "cuda" else "nccl"
+        return FusedAdamW(groups, lr=a.learning_rate, betas=(a.adam_beta1, a.adam_beta2), eps=a.adam_epsilon,
+                          weight_decay=a.weight_decay, state_dtype=sd, comm=self.comm, comm_mode=mode)
+
+    def get_train_dataloader(self):
+        return self.dataloader
+
+    # ---- hooks overridden per algorithm --------------------------------------------------------
+    def rollout(self, queries: torch.Tensor) -> Dict[str, torch.Tensor]:
+        a = self.args
+        seed = sampler_engine.next_rollout_seed() if a.changing_seed else a.seed
+        responses = sampler_engine.generate(self.samples_per_prompt, self.model, self.tokenizer, queries,
+                                            a.temperature, a.response_length, top_p=a.top_p,
+                                            seed=seed + self.comm.rank * 7919, backend=a.sampler,
+                                            rollout_dtype=a.rollout_dtype, kv_block_size=a.kv_block_size)
+        return {"responses": responses}
+
+    def score(self, queries: torch.Tensor, responses: torch.Tensor) -> torch.Tensor:
+        """Call the user reward callback exactly as the reference does (strings in, FloatTensor out)."""
+        n = responses.shape[0] // queries.shape[0]
+        if getattr(self.reward_func, "accepts_ids", False):
+            return self.reward_func(queries.repeat_interleave(n, 0), responses, self.tokenizer).to(self.device).float()
+        q_str = [q.replace(self.tokenizer.pad_token, "") for q in self.tokenizer.batch_decode(queries)]
+        r_str = self.tokenizer.batch_decode(responses)
+        self._last_strings = (q_str, r_str)
+        texts = [q_str[i // n] + r for i, r in enumerate(r_str)]
+        return self.reward_func(texts, self.tokenizer.eos_token).to(self.device).float()
+
+    def select_samples(self, queries, rollout, scores):
+        """Return dict(queries, responses, scores, log_scores[, seq_adv]) of the rows that are trained on."""
+        return {"queries": queries, "responses": rollout["responses"], "scores": scores, "log_scores": scores}
+
+    def token_rewards(self, sel, logprobs, ref_logprobs, seq_len, padding_mask, padding_mask_p1):
+        a = self.args
+        if self.kl_in_reward:
+            kl = logprobs - ref_logprobs
+            non_score = -a.kl_coef * kl
+        else:
+            non_score = torch.zeros_like(logprobs)
+        rewards = scatter_terminal_reward(non_score, sel["scores"], seq_len)
+        if a.whiten_rewards:
+            rewards = masked_whiten(rewards, mask=~padding_mask_p1, shift_mean=True)
+            rewards = torch.masked_fill(rewards, padding_mask_p1, 0)
+        return rewards, non_score
+
+    def after_rewards(self, R: Dict[str, torch.Tensor], roll: Dict[str, torch.Tensor]):
+        return R
+
+    def advantages(self, R):
+        """Default: discounted suffix-sum of the per-token rewards (REINFORCE / ReMax / GRPO)."""
+        a = self.args
+        adv = ops.discounted_suffix_sum(R["rewards"], a.gamma)
+        if a.advantage_whiten:
+            adv = masked_whiten(adv, ~R["padding_mask"])
+        return torch.masked_fill(adv, R["padding_mask"], 0), None
+
+    @staticmethod
+    def take_rows(R: Dict[str, torch.Tensor], idx: torch.Tensor) -> Dict[str, torch.Tensor]:
+        n = R["responses"].shape[0]
+        return {k: (v[idx] if isinstance(v, torch.Tensor) and v.dim() > 0 and v.shape[0] == n else v)
+                for k, v in R.items()}
+
+    def micro_loss(self, mb) -> (torch.Tensor, Dict[str, torch.Tensor]):
+        a = self.args
+        loss, st = ops.policy_loss_token(mb["new_logprobs"], mb["logprobs"], mb["advantages"], ~mb["padding_mask"],
+                                         a.cliprange)
+        st["pg_loss"] = loss.detach()
+        return loss, st
+
+    # ---- phase 4: no-grad logprob pass in token-budget chunks ----------------------------------
+    @torch.no_grad()
+    def logprob_pass(self, queries, responses):
+        a = self.args
+        ctx = queries.shape[1]
+        pad = self.tokenizer.pad_token_id
+        qr = torch.cat([queries, responses], 1)
+        lens = (qr != pad).sum(1).tolist()
+        # packed layout => the budget is on real tokens, not on padded rectangles
+        chunks = create_batches(lens, a.token_budget_fwd, mode="packed")
+        B, T_r = responses.shape
+        lp = torch.empty(B, T_r, dtype=torch.float32, device=self.device)
+        rlp = torch.empty_like(lp)
+        vals = torch.zeros_like(lp) if self.uses_value_model else None
+        self.policy.eval()
+        for idx in chunks:
+            ii = torch.as_tensor(idx, device=self.device)
+            out = response_logprobs(self.policy, qr[ii], ctx, pad, a.temperature, want_entropy=False,
+                                    value_model=self.model.value_model if self.uses_value_model else None)
+            lp[ii] = out[0]
+            if self.uses_value_model:
+                vals[ii] = out[2]
+            rlp[ii] = response_logprobs(self.ref_policy, qr[ii], ctx, pad, a.temperature, want_entropy=False)[0]
+        return qr, lp, rlp, vals
+
+    # ---- the update --------------------------------------------------------------------------
+    def train(self):
+        a = self.args
+        self.policy.train()
+        if not self._resumed:
+            self.state.global_step = 0
+            self.state.episode = 0
+            self._try_resume()
+        self.state.max_steps = a.num_total_batches * a.num_mini_batches          # (:444)
+        self.state.num_train_epochs = a.total_episodes / self.train_dataset_len
+        self.state.logging_steps, self.state.eval_steps, self.state.save_steps = a.logging_steps, a.eval_steps, a.save_steps
+        self.control = self.callback_handler.on_train_begin(a, self.state, self.control)
+        self.before_training()
+        it = iter(self.dataloader)
+        metrics = {}
+        start_update = self.state.global_step + 1
+        for update in range(start_update, a.num_total_batches + 1):
+            metrics = self.train_one_update(update, next(it))
+            self.lr_scheduler.step()
+            self.control = self.callback_handler.on_step_end(a, self.state, self.control)
+            # the reference's flow callback would stop at max_steps = batches*minibatches which is
+            # never reached (SURVEY.md 3.5 "Schedules"); the loop bound is authoritative here.
+            self.control.should_training_stop = False
+            if self.control.should_save:
+                with self.timer.phase("ckpt"):
+                    self._save_checkpoint(self.model, trial=None, metrics=metrics)
+                self.control = self.callback_handler.on_save(a, self.state, self.control)
+            self.after_update(update, metrics)
+        self.control = self.callback_handler.on_train_end(a, self.state, self.control)
+        if self.control.should_save:
+            self._save_checkpoint(self.model, trial=None, metrics=metrics)
+            self.control = self.callback_handler.on_save(a, self.state, self.control)
+        self.heartbeat.close()
+        return metrics
+
+    def before_training(self):
+        pass
+
+    def after_update(self, update: int, metrics: Dict[str, float]):
+        pass
+
+    def _phase(self, name: str, update: int):
+        self.heartbeat.beat(name, update)
+        maybe_inject(self.comm.rank, name, update)
+        return self.timer.phase(name)
+
+    def train_one_update(self, update: int, data) -> Dict[str, float]:
+        a = self.args
+        dev = self.device
+        pad = self.tokenizer.pad_token_id
+        t_start = time.time()
+        self.state.episode += a.batch_size
+        queries = data["input_ids"].to(dev)
+
+        with torch.no_grad():
+            with self._phase("offload", update):
+                self.tiering.evict("optimizer")                       # phase 1 (no-op when resident)
+            with self._phase("rollout", update):
+                rollout = self.rollout(queries)
+            with self._phase("reward", update):
+                scores_all = self.score(queries, rollout["responses"])
+                rollout = self.post_score(queries, rollout, scores_all)
+            rlhf_reward_mean = scores_all.mean()
+            sel = self.select_samples(queries, rollout, scores_all)
+            q, responses = sel["queries"], sel["responses"]
+            with self._phase("logprob", update):
+                self.tiering.fetch("ref")
+                qr, logprobs, ref_logprobs, values = self.logprob_pass(q, responses)
+                self.tiering.evict("ref")
+            with self._phase("advantage", update):
+                post = responses
+                if a.stop_token_id is not None:
+                    post = truncate_response(a.stop_token_id, pad, responses)
+                seq_len, padding_mask, padding_mask_p1 = response_masks(post, pad)
+                contain_eos = (post == self.tokenizer.eos_token_id).any(-1)
+                if a.missing_eos_penalty is not None:
+                    sel["scores"] = torch.where(contain_eos, sel["scores"], sel["scores"] - a.missing_eos_penalty)
+                logprobs = torch.masked_fill(logprobs, padding_mask, INVALID_LOGPROB)
+                ref_logprobs = torch.masked_fill(ref_logprobs, padding_mask, INVALID_LOGPROB)
+                if values is not None:
+                    values = torch.masked_fill(values, padding_mask_p1, 0)
+                rewards, non_score = self.token_rewards(sel, logprobs, ref_logprobs, seq_len, padding_mask, padding_mask_p1)
+                kl = logprobs - ref_logprobs
+                roll = dict(mean_kl=kl.sum(1).mean(), mean_entropy=(-logprobs).sum(1).mean(),
+                            non_score=non_score.sum(1).mean(),
+                            # PPO/REINFORCE/ReMax log non-score + score (ppo_trainer.py:800); GRPO the raw mean
+                            rlhf_reward=(non_score.sum(1).mean() + sel["log_scores"].mean()) if self.kl_in_reward
+                            else rlhf_reward_mean,
+                            scores=sel["log_scores"].mean(),
+                            num_eos=(responses == self.tokenizer.eos_token_id).sum())
+                R = dict(queries=q, responses=responses, query_responses=qr, logprobs=logprobs,
+                         ref_logprobs=ref_logprobs, values=values, padding_mask=padding_mask,
+                         padding_mask_p1=padding_mask_p1, seq_len=seq_len, rewards=rewards,
+                         scores=sel["scores"], log_scores=sel["log_scores"])
+                R = self.after_rewards(R, roll)          # RLOO / RAFT sub-select here
+                adv, returns = self.advantages(R)
+                check_finite("advantage", adv)
+            self.tiering.fetch("optimizer")
+
+        batch = {k: R[k] for k in ("query_responses", "responses", "logprobs", "ref_logprobs", "padding_mask",
+                                   "padding_mask_p1", "values")}
+        batch.update(advantages=adv, returns=returns, context_length=q.shape[1])
+        with self._phase("train", update):
+            stats = self.optimise(batch)
+
+        with torch.no_grad():
+            metrics = self.assemble_metrics(stats, roll)
+            self.log_completions(R)
+        secs = time.time() - t_start
+        metrics["time/s_per_episode"] = secs / a.batch_size          # the reference's printed number (:726)
+        metrics["throughput/episodes_per_s"] = a.batch_size / secs
+        metrics.update(self.timer.collect())
+        metrics["lr"] = self.lr_scheduler.get_last_lr()[0] if hasattr(self.lr_scheduler, "get_last_lr") else \
+            self.optimizer.param_groups[0]["lr"]
+        metrics["episode"] = self.state.episode
+        self.state.epoch = self.state.episode / self.train_dataset_len
+        self.state.global_step += 1
+        self.log(metrics)
+        return metrics
+
+    def post_score(self, queries, rollout, scores):
+        return rollout
+
+    # ---- phase 6 ------------------------------------------------------------------------------
+    def optimise(self, batch) -> Dict[str, torch.Tensor]:
+        a = self.args
+        ctx = batch["context_length"]
+        pad = self.tokenizer.pad_token_id
+        shape = (a.num_ppo_epochs, a.num_mini_batches, a.gradient_accumulation_steps)
+        stats = defaultdict(lambda: torch.zeros(shape, device=self.device))
+        n_local = batch["responses"].shape[0]
+        self.policy.train()
+        for ep in range(a.num_ppo_epochs):
+            b_inds = self._np_rng.permutation(n_local)
+            for mi, mb_start in enumerate(range(0, n_local, a.local_mini_batch_size)):
+                mini = b_inds[mb_start:mb_start + a.local_mini_batch_size]
+                self.optimizer.zero_grad()
+                for gi, mc_start in enumerate(range(0, len(mini), a.per_device_train_batch_size)):
+                    inds = torch.as_tensor(mini[mc_start:mc_start + a.per_device_train_batch_size], device=self.device)
+                    mb = {k: (v[inds] if isinstance(v, torch.Tensor) and v.dim() > 0 and v.shape[0] == n_local else v)
+                          for k, v in batch.items()}
+                    out = response_logprobs(self.policy, mb["query_responses"], ctx, pad, a.temperature,
+                                            want_entropy=True,
+                                            value_model=self.model.value_model if self.uses_value_model else None)
+                    new_lp = torch.masked_fill(out[0], mb["padding_mask"], INVALID_LOGPROB)
+                    mb["new_logprobs"] = new_lp
+                    if self.uses_value_model:
+                        mb["vpred"] = out[2]
+                    loss, st = self.micro_loss(mb)
+                    (loss / a.gradient_accumulation_steps).backward()
+                    with torch.no_grad():
+                        ent = out[1]
+                        if a.stats_include_padding:
+                            st["entropy"] = ent.mean()
+                        else:
+                            m = (~mb["padding_mask"]).float()
+                            st["entropy"] = (ent * m).sum() / m.sum().clamp_min(1)
+                        for k, v in st.items():
+                            stats[k][ep, mi, gi] = v
+                self.optimizer.step()
+        self.optimizer.zero_grad()
+        return stats
+
+    # ---- metrics ------------------------------------------------------------------------------
+    def assemble_metrics(self, stats, roll) -> Dict[str, float]:
+        a = self.args
+        inc = a.stats_include_padding
+        local = {
+            "objective/kl_old": float(self.kl_metric(stats, roll)),
+            "objective/entropy_old": float(roll["mean_entropy"]),
+            "objective/non_score_reward_old": float(roll["non_score"]) if self.kl_in_reward else 0.0,
+            "eval_objective/rlhf_reward_old": float(roll["rlhf_reward"]),
+            "eval_objective/scores_old": float(roll["scores"]),
+            "loss/policy_avg_new": float(stats["pg_loss"].mean()),
+            "policy/entropy_avg_new": float(stats["entropy"].mean()),
+        }
+        if self.logs_policy_ratio_stats:
+            local["policy/approxkl_avg_new"] = float(stats["approxkl_all" if inc else "approxkl_masked"].mean())
+            local["policy/clipfrac_avg_new"] = float(stats["clipfrac"].mean())
+            local["val/ratio_new"] = float(stats["ratio_mean_all" if inc else "ratio_mean_masked"].mean())
+        if self.uses_value_model:
+            local["loss/value_avg_new"] = float(stats["vf_loss"].mean())
+            local["val/clipfrac_avg_new"] = float(stats["vf_clipfrac"].mean())
+            local["eval_accuracy_new"] = 0.0
+        out = self.comm.reduce_scalars(local, "mean")                     # ONE packed all-reduce (K23)
+        if self.logs_policy_ratio_stats:
+            r = stats["ratio_mean_all" if inc else "ratio_mean_masked"].reshape(-1)
+            allr = self.comm.all_gather_cat(r)
+            out["val/ratio_var_new"] = float(allr.var()) if allr.numel() > 1 else 0.0
+        out["val/num_eos_tokens_old"] = int(roll["num_eos"])
+        return out
+
+    def kl_metric(self, stats, roll):
+        return roll["mean_kl"]
+
+    def log(self, metrics: Dict[str, float]):
+        logs = dict(metrics)
+        logs["epoch"] = round(self.state.epoch, 6)
+        logs["step"] = self.state.global_step
+        self.state.log_history.append(logs)
+        self.control = self.callback_handler.on_log(self.args, self.state, self.control, logs)
+
+    def log_completions(self, sel):
+        """5-row completions table (reference: grpo_trainer.py:712-724)."""
+        a = self.args
+        if not self.comm.is_main or a.num_sample_generations == 0:
+            return
+        k = min(5, sel["responses"].shape[0])
+        q = [s.replace(self.tokenizer.pad_token, "") for s in self.tokenizer.batch_decode(sel["queries"][:k])]
+        r = self.tokenizer.batch_decode(sel["responses"][:k])
+        sc = sel["log_scores"][:k].tolist()
+        rows = [[q[i], r[i], sc[i], sc[i]] for i in range(k)]
+        self.last_completions = rows
+        print_rich_table(["query", "response", "score", "rlhf_score"], rows)
+        for cb in self.callback_handler.callbacks:
+            if hasattr(cb, "log_table"):
+                cb.log_table("completions", ["query", "response", "score", "rlhf_score"], rows)
+
+    # ---- checkpointing (runtime/checkpoint.py holds the format) ---------------------------------
+    def save_model(self, output_dir: Optional[str] = None, _internal_call: bool = False):
+        ckpt.save_model(self, output_dir or self.args.output_dir)
+
+    def _save_checkpoint(self, model, trial=None, metrics=None):
+        ckpt.save_checkpoint(self, metrics)
+
+    def _try_resume(self):
+        a = self.args
+        if a.resume == "never":
+            return
+        path = ckpt.find_resume_checkpoint(a) if a.resume == "auto" else a.resume
+        if path:
+            ckpt.load_checkpoint(self, path)
+            self._resumed = True
+            if self.comm.is_main:
+                print(f"[resume] restored {path} at global_step={self.state.global_step}")
