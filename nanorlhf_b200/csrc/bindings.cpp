@@ -1,0 +1,347 @@
+// Python bindings (pybind11 via torch extension headers) for the sm_100a kernels.
+// Kernels live in plain .cu translation units with a C launch API (kernels.h, gemm_sm100.h); this file
+// only validates tensors, builds TMA descriptors and forwards the current CUDA stream.
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <torch/extension.h>
+
+#include <tuple>
+#include <vector>
+
+#include "gemm_sm100.h"
+#include "kernels.h"
+#include "runtime.h"
+#include "tma_host.h"
+
+namespace {
+
+inline cudaStream_t cur_stream() { return at::cuda::getCurrentCUDAStream().stream(); }
+
+inline void check(cudaError_t e, const char* what) {
+  TORCH_CHECK(e == cudaSuccess, what, ": ", cudaGetErrorString(e));
+}
+
+inline void check_bf16_2d(const torch::Tensor& t, const char* name) {
+  TORCH_CHECK(t.is_cuda() && t.scalar_type() == torch::kBFloat16 && t.dim() == 2, name, " must be a 2D CUDA bf16 tensor");
+  TORCH_CHECK(t.stride(1) == 1 && (t.stride(0) * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(t.data_ptr()) & 15) == 0,
+              name, " must be row-major with 16-byte aligned rows");
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
+int pick_block_n(int64_t M, int64_t N) {
+  // 256-wide tiles unless that leaves most SMs idle
+  int64_t tiles256 = ((M + 127) / 128) * ((N + 255) / 256);
+  if (N <= 128 || tiles256 < num_sms() / 2) return 128;
+  return 256;
+}
+
+// D[M,N] = A[M,K] @ B[N,K]^T (+ bias[N])
+torch::Tensor gemm_bf16(const torch::Tensor& a, const torch::Tensor& b, const c10::optional<torch::Tensor>& bias,
+                        c10::optional<torch::Tensor> out_opt, int64_t block_n) {
+  check_bf16_2d(a, "a");
+  check_bf16_2d(b, "b");
+  const int64_t M = a.size(0), K = a.size(1), N = b.size(0);
+  TORCH_CHECK(b.size(1) == K, "inner dimensions differ");
+  TORCH_CHECK(K % 8 == 0 && N % 8 == 0, "K and N must be multiples of 8");
+  c10::cuda::CUDAGuard guard(a.device());
+  torch::Tensor out = out_opt.has_value() ? *out_opt : torch::empty({M, N}, a.options());
+  check_bf16_2d(out, "out");
+  TORCH_CHECK(out.size(0) == M && out.size(1) == N, "out has the wrong shape");
+  if (M == 0) return out;
+  const int bn = block_n > 0 ? static_cast<int>(block_n) : pick_block_n(M, N);
+  CUtensorMap tmA = nrl::make_tma_2d(a.data_ptr(), M, K, a.stride(0) * 2, 128, 64, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2);
+  CUtensorMap tmB = nrl::make_tma_2d(b.data_ptr(), N, K, b.stride(0) * 2, bn, 64, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2);
+  CUtensorMap tmD = nrl::make_tma_2d(out.data_ptr(), M, N, out.stride(0) * 2, 128, 64, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2);
+  nrl::GemmParams p{};
+  p.M = M; p.N = N; p.K = K; p.n_splits = 1; p.scale = 1.f;
+  if (bias.has_value()) {
+    TORCH_CHECK(bias->is_cuda() && bias->scalar_type() == torch::kBFloat16 && bias->numel() == N && bias->is_contiguous(),
+                "bias must be a contiguous CUDA bf16 [N] tensor");
+    p.bias = reinterpret_cast<const __nv_bfloat16*>(bias->data_ptr());
+  }
+  check(nrl_gemm_bf16_tn(&tmA, &tmB, &tmD, &p, bn, nrl::EPI_STORE, num_sms(), cur_stream()), "gemm_bf16");
+  return out;
+}
+
+int pick_splits(int64_t M, int64_t N, int bn) {
+  int64_t num_m = (M + 127) / 128, num_n = (N + bn - 1) / bn;
+  int64_t s = (num_sms() + num_m - 1) / num_m;       // enough work items to cover the SMs
+  if (num_m >= num_sms()) s = 1;
+  s = std::max<int64_t>(1, std::min<int64_t>(s, std::min<int64_t>(num_n, 64)));
+  return static_cast<int>(s);
+}
+
+// fused lm-head log-prob forward: returns (logp, entropy, lse), all fp32 [M]
+std::tuple<torch::Tensor, torch::Tensor, torch::Tensor> lmhead_logprob_fwd(const torch::Tensor& hidden,
+                                                                          const torch::Tensor& weight,
+                                                                          const torch::Tensor& targets,
+                                                                          double inv_temperature, int64_t n_splits) {
+  check_bf16_2d(hidden, "hidden");
+  check_bf16_2d(weight, "weight");
+  const int64_t M = hidden.size(0), K = hidden.size(1), V = weight.size(0);
+  TORCH_CHECK(weight.size(1) == K && K % 8 == 0);
+  TORCH_CHECK(targets.is_cuda() && targets.scalar_type() == torch::kInt32 && targets.numel() == M && targets.is_contiguous(),
+              "targets must be contiguous CUDA int32 [M]");
+  c10::cuda::CUDAGuard guard(hidden.device());
+  auto fopt = hidden.options().dtype(torch::kFloat32);
+  torch::Tensor logp = torch::empty({M}, fopt), ent = torch::empty({M}, fopt), lse = torch::empty({M}, fopt);
+  if (M == 0) return {logp, ent, lse};
+  const int bn = 256;
+  const int splits = n_splits > 0 ? static_cast<int>(n_splits) : pick_splits(M, V, bn);
+  torch::Tensor partials = torch::empty({splits, M, 4}, fopt);
+  CUtensorMap tmA = nrl::make_tma_2d(hidden.data_ptr(), M, K, hidden.stride(0) * 2, 128, 64, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2);
+  CUtensorMap tmB = nrl::make_tma_2d(weight.data_ptr(), V, K, weight.stride(0) * 2, bn, 64, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2);
+  nrl::GemmParams p{};
+  p.M = M; p.N = V; p.K = K; p.n_splits = splits; p.scale = static_cast<float>(inv_temperature);
+  p.targets = targets.data_ptr<int>();
+  p.partials = partials.data_ptr<float>();
+  check(nrl_gemm_bf16_tn(&tmA, &tmB, &tmA, &p, bn, nrl::EPI_LOGPROB, num_sms(), cur_stream()), "lmhead_logprob_fwd");
+  check(nrl_lmhead_combine(partials.data_ptr<float>(), M, splits, logp.data_ptr<float>(), ent.data_ptr<float>(),
+                           lse.data_ptr<float>(), cur_stream()), "lmhead_combine");
+  return {logp, ent, lse};
+}
+
+// K-LP backward, stage 1: dZ[M,V] = (onehot - softmax) * grad_logp / T, recomputed through the tensor cores
+torch::Tensor lmhead_dlogits(const torch::Tensor& hidden, const torch::Tensor& weight, const torch::Tensor& targets,
+                             const torch::Tensor& lse, const torch::Tensor& grad_logp, double inv_temperature) {
+  check_bf16_2d(hidden, "hidden");
+  check_bf16_2d(weight, "weight");
+  const int64_t M = hidden.size(0), K = hidden.size(1), V = weight.size(0);
+  TORCH_CHECK(V % 8 == 0 && K % 8 == 0);
+  TORCH_CHECK(targets.scalar_type() == torch::kInt32 && lse.scalar_type() == torch::kFloat32 &&
+              grad_logp.scalar_type() == torch::kFloat32 && lse.is_contiguous() && grad_logp.is_contiguous());
+  c10::cuda::CUDAGuard guard(hidden.device());
+  torch::Tensor dz = torch::empty({M, V}, hidden.options());
+  if (M == 0) return dz;
+  const int bn = 256;
+  CUtensorMap tmA = nrl::make_tma_2d(hidden.data_ptr(), M, K, hidden.stride(0) * 2, 128, 64, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2);
+  CUtensorMap tmB = nrl::make_tma_2d(weight.data_ptr(), V, K, weight.stride(0) * 2, bn, 64, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2);
+  CUtensorMap tmD = nrl::make_tma_2d(dz.data_ptr(), M, V, dz.stride(0) * 2, 128, 64, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2);
+  nrl::GemmParams p{};
+  p.M = M; p.N = V; p.K = K; p.n_splits = 1; p.scale = static_cast<float>(inv_temperature);
+  p.targets = targets.data_ptr<int>();
+  p.lse = lse.data_ptr<float>();
+  p.grad_logp = grad_logp.data_ptr<float>();
+  check(nrl_gemm_bf16_tn(&tmA, &tmB, &tmD, &p, bn, nrl::EPI_DLOGITS, num_sms(), cur_stream()), "lmhead_dlogits");
+  return dz;
+}
+
+// ---- elementwise --------------------------------------------------------------------------------
+std::tuple<torch::Tensor, torch::Tensor, torch::Tensor> rmsnorm(const torch::Tensor& x, const torch::Tensor& w, double eps,
+                                                                const c10::optional<torch::Tensor>& residual,
+                                                                bool want_rstd) {
+  TORCH_CHECK(x.is_cuda() && x.scalar_type() == torch::kBFloat16 && x.is_contiguous() && x.dim() == 2);
+  TORCH_CHECK(w.scalar_type() == torch::kBFloat16 && w.is_contiguous() && w.numel() == x.size(1));
+  c10::cuda::CUDAGuard guard(x.device());
+  const int rows = x.size(0), d = x.size(1);
+  torch::Tensor y = torch::empty_like(x);
+  torch::Tensor res_out, rstd;
+  const void* res_ptr = nullptr;
+  void* res_out_ptr = nullptr;
+  if (residual.has_value()) {
+    TORCH_CHECK(residual->is_contiguous() && residual->sizes() == x.sizes() && residual->scalar_type() == torch::kBFloat16);
+    res_out = torch::empty_like(x);
+    res_ptr = residual->data_ptr();
+    res_out_ptr = res_out.data_ptr();
+  }
+  if (want_rstd) rstd = torch::empty({rows}, x.options().dtype(torch::kFloat32));
+  check(nrl_rmsnorm(x.data_ptr(), res_ptr, w.data_ptr(), y.data_ptr(), res_out_ptr,
+                    want_rstd ? rstd.data_ptr<float>() : nullptr, rows, d, static_cast<float>(eps), cur_stream()), "rmsnorm");
+  return {y, res_out, rstd};
+}
+
+torch::Tensor rmsnorm_bwd(const torch::Tensor& x, const torch::Tensor& w, const torch::Tensor& gy, const torch::Tensor& rstd) {
+  TORCH_CHECK(x.is_contiguous() && gy.is_contiguous() && x.scalar_type() == torch::kBFloat16 && gy.scalar_type() == torch::kBFloat16);
+  c10::cuda::CUDAGuard guard(x.device());
+  torch::Tensor gx = torch::empty_like(x);
+  check(nrl_rmsnorm_bwd(x.data_ptr(), w.data_ptr(), gy.data_ptr(), rstd.data_ptr<float>(), gx.data_ptr(), x.size(0), x.size(1), cur_stream()),
+        "rmsnorm_bwd");
+  return gx;
+}
+
+// x: [T, H, D] (last two dims contiguous, arbitrary token stride); cos/sin: [T, D/2] fp32
+torch::Tensor rope(const torch::Tensor& x, const torch::Tensor& cos_t, const torch::Tensor& sin_t, double sin_sign, bool inplace) {
+  TORCH_CHECK(x.is_cuda() && x.scalar_type() == torch::kBFloat16 && x.dim() == 3 && x.stride(2) == 1 && x.stride(1) == x.size(2));
+  TORCH_CHECK(cos_t.scalar_type() == torch::kFloat32 && cos_t.is_contiguous() && sin_t.is_contiguous() &&
+              cos_t.size(0) == x.size(0) && cos_t.size(1) * 2 == x.size(2));
+  c10::cuda::CUDAGuard guard(x.device());
+  torch::Tensor y = inplace ? x : torch::empty({x.size(0), x.size(1), x.size(2)}, x.options());
+  check(nrl_rope(x.data_ptr(), y.data_ptr(), cos_t.data_ptr<float>(), sin_t.data_ptr<float>(), x.size(0), x.size(1), x.size(2),
+                 x.stride(0), y.stride(0), static_cast<float>(sin_sign), cur_stream()), "rope");
+  return y;
+}
+
+torch::Tensor swiglu(const torch::Tensor& gu) {
+  TORCH_CHECK(gu.is_cuda() && gu.scalar_type() == torch::kBFloat16 && gu.is_contiguous() && gu.dim() == 2 && gu.size(1) % 16 == 0);
+  c10::cuda::CUDAGuard guard(gu.device());
+  torch::Tensor out = torch::empty({gu.size(0), gu.size(1) / 2}, gu.options());
+  check(nrl_swiglu(gu.data_ptr(), out.data_ptr(), gu.size(0), gu.size(1) / 2, cur_stream()), "swiglu");
+  return out;
+}
+
+torch::Tensor swiglu_bwd(const torch::Tensor& gu, const torch::Tensor& gout) {
+  TORCH_CHECK(gu.is_contiguous() && gout.is_contiguous() && gout.scalar_type() == torch::kBFloat16);
+  c10::cuda::CUDAGuard guard(gu.device());
+  torch::Tensor dgu = torch::empty_like(gu);
+  check(nrl_swiglu_bwd(gu.data_ptr(), gout.data_ptr(), dgu.data_ptr(), gu.size(0), gu.size(1) / 2, cur_stream()), "swiglu_bwd");
+  return dgu;
+}
+
+// ---- RL kernels -----------------------------------------------------------------------------------
+std::tuple<torch::Tensor, torch::Tensor> gae_scan(const torch::Tensor& rewards, const c10::optional<torch::Tensor>& values,
+                                                  double gamma, double lam) {
+  TORCH_CHECK(rewards.is_cuda() && rewards.scalar_type() == torch::kFloat32 && rewards.is_contiguous() && rewards.dim() == 2);
+  c10::cuda::CUDAGuard guard(rewards.device());
+  torch::Tensor adv = torch::empty_like(rewards), ret;
+  const float* vptr = nullptr;
+  float* rptr = nullptr;
+  if (values.has_value()) {
+    TORCH_CHECK(values->is_contiguous() && values->scalar_type() == torch::kFloat32 && values->sizes() == rewards.sizes());
+    ret = torch::empty_like(rewards);
+    vptr = values->data_ptr<float>();
+    rptr = ret.data_ptr<float>();
+  }
+  check(nrl_gae_scan(rewards.data_ptr<float>(), vptr, adv.data_ptr<float>(), rptr, rewards.size(0), rewards.size(1),
+                     static_cast<float>(gamma), static_cast<float>(lam), cur_stream()), "gae_scan");
+  return {adv, ret};
+}
+
+// returns (grad_unnorm [n] fp32, acc [10] fp32)
+std::tuple<torch::Tensor, torch::Tensor> policy_loss(const torch::Tensor& new_lp, const torch::Tensor& old_lp,
+                                                     const torch::Tensor& adv, const torch::Tensor& mask,
+                                                     const c10::optional<torch::Tensor>& ref_lp, double cliprange,
+                                                     double kl_coef) {
+  for (const auto* t : {&new_lp, &old_lp, &adv})
+    TORCH_CHECK(t->is_cuda() && t->scalar_type() == torch::kFloat32 && t->is_contiguous());
+  TORCH_CHECK(mask.scalar_type() == torch::kBool && mask.is_contiguous() && mask.numel() == new_lp.numel());
+  c10::cuda::CUDAGuard guard(new_lp.device());
+  torch::Tensor grad = torch::empty_like(new_lp);
+  torch::Tensor acc = torch::zeros({10}, new_lp.options());
+  const float* rp = nullptr;
+  if (ref_lp.has_value()) {
+    TORCH_CHECK(ref_lp->is_contiguous() && ref_lp->scalar_type() == torch::kFloat32);
+    rp = ref_lp->data_ptr<float>();
+  }
+  check(nrl_policy_loss(new_lp.data_ptr<float>(), old_lp.data_ptr<float>(), adv.data_ptr<float>(),
+                        reinterpret_cast<const uint8_t*>(mask.data_ptr<bool>()), rp, static_cast<float>(cliprange),
+                        static_cast<float>(kl_coef), new_lp.numel(), grad.data_ptr<float>(), acc.data_ptr<float>(), cur_stream()),
+        "policy_loss");
+  return {grad, acc};
+}
+
+std::tuple<torch::Tensor, torch::Tensor> value_loss(const torch::Tensor& vpred, const torch::Tensor& vold,
+                                                    const torch::Tensor& ret, const torch::Tensor& mask, double clip) {
+  for (const auto* t : {&vpred, &vold, &ret})
+    TORCH_CHECK(t->is_cuda() && t->scalar_type() == torch::kFloat32 && t->is_contiguous());
+  TORCH_CHECK(mask.scalar_type() == torch::kBool && mask.is_contiguous());
+  c10::cuda::CUDAGuard guard(vpred.device());
+  torch::Tensor grad = torch::empty_like(vpred);
+  torch::Tensor acc = torch::zeros({4}, vpred.options());
+  check(nrl_value_loss(vpred.data_ptr<float>(), vold.data_ptr<float>(), ret.data_ptr<float>(),
+                       reinterpret_cast<const uint8_t*>(mask.data_ptr<bool>()), static_cast<float>(clip), vpred.numel(),
+                       grad.data_ptr<float>(), acc.data_ptr<float>(), cur_stream()), "value_loss");
+  return {grad, acc};
+}
+
+void adamw_flat(torch::Tensor param, const torch::Tensor& grad, torch::Tensor m, torch::Tensor v, double lr, double beta1,
+                double beta2, double eps, double wd, int64_t step, double grad_scale) {
+  TORCH_CHECK(param.is_cuda() && param.scalar_type() == torch::kBFloat16 && grad.scalar_type() == torch::kBFloat16);
+  TORCH_CHECK(param.is_contiguous() && grad.is_contiguous() && m.is_contiguous() && v.is_contiguous());
+  TORCH_CHECK(m.scalar_type() == v.scalar_type() && (m.scalar_type() == torch::kFloat32 || m.scalar_type() == torch::kBFloat16));
+  TORCH_CHECK(param.numel() == grad.numel() && param.numel() == m.numel() && param.numel() == v.numel());
+  c10::cuda::CUDAGuard guard(param.device());
+  nrl::AdamHyper h;
+  h.lr = lr; h.beta1 = beta1; h.beta2 = beta2; h.eps = eps; h.wd = wd;
+  h.step_size = static_cast<float>(lr / (1.0 - std::pow(beta1, static_cast<double>(step))));
+  h.inv_bc2 = static_cast<float>(1.0 / (1.0 - std::pow(beta2, static_cast<double>(step))));
+  h.grad_scale = grad_scale;
+  check(nrl_adamw_flat(param.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(), param.numel(),
+                       m.scalar_type() == torch::kBFloat16 ? 1 : 0, h, cur_stream()), "adamw_flat");
+}
+
+// ---- sampler kernels ------------------------------------------------------------------------------
+torch::Tensor sample(const torch::Tensor& logits, double temperature, double top_p, int64_t seed, int64_t step,
+                     const c10::optional<torch::Tensor>& row_ids, c10::optional<torch::Tensor> out_opt) {
+  TORCH_CHECK(logits.is_cuda() && logits.dim() == 2 && logits.stride(1) == 1);
+  const bool bf16 = logits.scalar_type() == torch::kBFloat16;
+  TORCH_CHECK(bf16 || logits.scalar_type() == torch::kFloat32);
+  TORCH_CHECK((logits.stride(0) * logits.element_size()) % 16 == 0, "logit rows must be 16-byte aligned");
+  c10::cuda::CUDAGuard guard(logits.device());
+  torch::Tensor out = out_opt.has_value() ? *out_opt : torch::empty({logits.size(0)}, logits.options().dtype(torch::kInt32));
+  const int* rid = nullptr;
+  if (row_ids.has_value()) rid = row_ids->data_ptr<int>();
+  check(nrl_sample(logits.data_ptr(), bf16 ? 1 : 0, logits.stride(0), logits.size(0), logits.size(1),
+                   static_cast<float>(temperature), static_cast<float>(top_p), static_cast<unsigned long long>(seed),
+                   static_cast<unsigned long long>(step), rid, out.data_ptr<int>(), cur_stream()), "sample");
+  return out;
+}
+
+void kv_cache_write(const torch::Tensor& k, const torch::Tensor& v, torch::Tensor k_cache, torch::Tensor v_cache,
+                    const torch::Tensor& slot_mapping) {
+  TORCH_CHECK(k.dim() == 3 && v.dim() == 3 && k.stride(2) == 1 && k.stride(1) == k.size(2) && v.stride(2) == 1 && v.stride(1) == v.size(2));
+  TORCH_CHECK(k_cache.dim() == 4 && k_cache.is_contiguous() && v_cache.is_contiguous());
+  TORCH_CHECK(slot_mapping.scalar_type() == torch::kInt32 && slot_mapping.numel() == k.size(0));
+  c10::cuda::CUDAGuard guard(k.device());
+  check(nrl_kv_cache_write(k.data_ptr(), v.data_ptr(), k.stride(0), v.stride(0), k_cache.data_ptr(), v_cache.data_ptr(),
+                           slot_mapping.data_ptr<int>(), k.size(0), k.size(1), k.size(2), k_cache.size(2), cur_stream()),
+        "kv_cache_write");
+}
+
+torch::Tensor paged_decode(const torch::Tensor& q, const torch::Tensor& k_cache, const torch::Tensor& v_cache,
+                           const torch::Tensor& block_tables, const torch::Tensor& context_lens, double scale,
+                           int64_t splits, c10::optional<torch::Tensor> out_opt) {
+  TORCH_CHECK(q.is_cuda() && q.scalar_type() == torch::kBFloat16 && q.dim() == 3 && q.stride(2) == 1 && q.stride(1) == q.size(2));
+  TORCH_CHECK(block_tables.scalar_type() == torch::kInt32 && block_tables.is_contiguous() && context_lens.scalar_type() == torch::kInt32);
+  c10::cuda::CUDAGuard guard(q.device());
+  const int S = q.size(0), Hq = q.size(1), D = q.size(2), Hkv = k_cache.size(1);
+  torch::Tensor out = out_opt.has_value() ? *out_opt : torch::empty({S, Hq, D}, q.options());
+  torch::Tensor po, pml;
+  float *pop = nullptr, *pmlp = nullptr;
+  if (splits > 1) {
+    po = torch::empty({S, Hkv, splits, 8, D}, q.options().dtype(torch::kFloat32));
+    pml = torch::empty({S, Hkv, splits, 8, 2}, q.options().dtype(torch::kFloat32));
+    pop = po.data_ptr<float>();
+    pmlp = pml.data_ptr<float>();
+  }
+  check(nrl_paged_decode(q.data_ptr(), q.stride(0), k_cache.data_ptr(), v_cache.data_ptr(), block_tables.data_ptr<int>(),
+                         context_lens.data_ptr<int>(), out.data_ptr(), pop, pmlp, S, Hq, Hkv, D, k_cache.size(2),
+                         block_tables.size(1), static_cast<int>(splits), static_cast<float>(scale), cur_stream()),
+        "paged_decode");
+  return out;
+}
+
+}  // namespace
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  m.doc() = "nanorlhf_b200 sm_100a kernels";
+  m.def("gemm_bf16", &gemm_bf16, py::arg("a"), py::arg("b"), py::arg("bias") = py::none(), py::arg("out") = py::none(),
+        py::arg("block_n") = 0);
+  m.def("lmhead_logprob_fwd", &lmhead_logprob_fwd, py::arg("hidden"), py::arg("weight"), py::arg("targets"),
+        py::arg("inv_temperature"), py::arg("n_splits") = 0);
+  m.def("lmhead_dlogits", &lmhead_dlogits);
+  m.def("rmsnorm", &rmsnorm, py::arg("x"), py::arg("w"), py::arg("eps"), py::arg("residual") = py::none(),
+        py::arg("want_rstd") = false);
+  m.def("rmsnorm_bwd", &rmsnorm_bwd);
+  m.def("rope", &rope, py::arg("x"), py::arg("cos"), py::arg("sin"), py::arg("sin_sign") = 1.0, py::arg("inplace") = false);
+  m.def("swiglu", &swiglu);
+  m.def("swiglu_bwd", &swiglu_bwd);
+  m.def("gae_scan", &gae_scan, py::arg("rewards"), py::arg("values") = py::none(), py::arg("gamma") = 1.0, py::arg("lam") = 1.0);
+  m.def("policy_loss", &policy_loss);
+  m.def("value_loss", &value_loss);
+  m.def("adamw_flat", &adamw_flat);
+  m.def("sample", &sample, py::arg("logits"), py::arg("temperature"), py::arg("top_p"), py::arg("seed"), py::arg("step"),
+        py::arg("row_ids") = py::none(), py::arg("out") = py::none());
+  m.def("kv_cache_write", &kv_cache_write);
+  m.def("paged_decode", &paged_decode, py::arg("q"), py::arg("k_cache"), py::arg("v_cache"), py::arg("block_tables"),
+        py::arg("context_lens"), py::arg("scale"), py::arg("splits") = 1, py::arg("out") = py::none());
+  nrl::bind_runtime(m);
+}

@@ -1,0 +1,32 @@
+// Host-visible parameter block + epilogue selectors of the tcgen05 GEMM family (gemm_sm100.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+namespace nrl {
+
+enum GemmEpilogue : int {
+  EPI_STORE = 0,     // D = A B^T (+ bias)                      -> bf16 [M,N]
+  EPI_LOGPROB = 1,   // fused lm-head log-prob partials          -> float4 [n_splits, M]
+  EPI_DLOGITS = 2,   // dZ = (onehot - softmax) * g / T          -> bf16 [M,N]
+};
+
+struct GemmParams {
+  int M, N, K;
+  int n_splits;                 // EPI_LOGPROB: vocab splits (work items = m_tiles * n_splits)
+  float scale;                  // 1 / temperature for the log-prob epilogues
+  const __nv_bfloat16* bias;    // EPI_STORE: optional [N]
+  const int* targets;           // EPI_LOGPROB / EPI_DLOGITS: [M] int32
+  const float* lse;             // EPI_DLOGITS: [M]
+  const float* grad_logp;       // EPI_DLOGITS: [M]
+  float* partials;              // EPI_LOGPROB: [n_splits, M, 4]
+};
+
+}  // namespace nrl
+
+extern "C" cudaError_t nrl_gemm_bf16_tn(const CUtensorMap* tmA, const CUtensorMap* tmB, const CUtensorMap* tmD,
+                                        const nrl::GemmParams* p, int block_n, int epi, int num_sms,
+                                        cudaStream_t stream);
+extern "C" cudaError_t nrl_lmhead_combine(const float* partials, int M, int n_splits, float* logp, float* entropy,
+                                          float* lse, cudaStream_t stream);

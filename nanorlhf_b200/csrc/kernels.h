@@ -1,0 +1,48 @@
+// C launch API of the non-GEMM kernels (elementwise.cu, rl_kernels.cu, sampling.cu, attention.cu, comm.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace nrl {
+struct AdamHyper {
+  float lr, beta1, beta2, eps, wd;
+  float step_size;    // lr / (1 - beta1^t)
+  float inv_bc2;      // 1 / (1 - beta2^t)
+  float grad_scale;   // multiplies the gradient before use (1/world, 1/accum ...)
+};
+}  // namespace nrl
+
+extern "C" {
+cudaError_t nrl_rmsnorm(const void* x, const void* residual, const void* w, void* y, void* residual_out, float* rstd,
+                        int rows, int d, float eps, cudaStream_t s);
+cudaError_t nrl_rmsnorm_bwd(const void* x, const void* w, const void* gy, const float* rstd, void* gx, int rows, int d,
+                            cudaStream_t s);
+cudaError_t nrl_rope(const void* x, void* y, const float* cos_t, const float* sin_t, int T, int H, int D,
+                     long x_stride_t, long y_stride_t, float sin_sign, cudaStream_t s);
+cudaError_t nrl_swiglu(const void* gu, void* out, long T, int F, cudaStream_t s);
+cudaError_t nrl_swiglu_bwd(const void* gu, const void* gout, void* dgu, long T, int F, cudaStream_t s);
+
+cudaError_t nrl_gae_scan(const float* rewards, const float* values, float* adv, float* returns, int B, int T,
+                         float gamma, float lam, cudaStream_t s);
+cudaError_t nrl_policy_loss(const float* new_lp, const float* old_lp, const float* adv, const uint8_t* mask,
+                            const float* ref_lp, float cliprange, float kl_coef, long n, float* grad_unnorm,
+                            float* acc, cudaStream_t s);
+cudaError_t nrl_value_loss(const float* vpred, const float* vold, const float* ret, const uint8_t* mask, float clip,
+                           long n, float* grad_unnorm, float* acc, cudaStream_t s);
+cudaError_t nrl_adamw_flat(void* param, const void* grad, void* m, void* v, long n, int moments_bf16,
+                           nrl::AdamHyper h, cudaStream_t s);
+
+cudaError_t nrl_sample(const void* logits, int is_bf16, long row_stride, int rows, int V, float temperature,
+                       float top_p, unsigned long long seed, unsigned long long step, const int* row_ids,
+                       int* out_tokens, cudaStream_t s);
+}
+
+extern "C" {
+cudaError_t nrl_kv_cache_write(const void* k, const void* v, long k_stride_t, long v_stride_t, void* k_cache,
+                               void* v_cache, const int* slot_mapping, int T, int Hkv, int head_dim, int page,
+                               cudaStream_t s);
+cudaError_t nrl_paged_decode(const void* q, long q_stride_s, const void* k_cache, const void* v_cache,
+                             const int* block_tables, const int* context_lens, void* out, float* part_o,
+                             float* part_ml, int S, int Hq, int Hkv, int head_dim, int page, int max_blocks, int splits,
+                             float scale, cudaStream_t s);
+}

@@ -1,0 +1,43 @@
+// Host helper: build CUtensorMap descriptors without linking libcuda (driver entry point lookup).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cudaTypedefs.h>
+#include <stdexcept>
+#include <string>
+
+namespace nrl {
+
+inline PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || ptr == nullptr)
+      throw std::runtime_error("cuTensorMapEncodeTiled entry point unavailable");
+    fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+  }
+  return fn;
+}
+
+// 2D row-major tensor [rows, cols] of `elem_bytes`-wide elements, box [box_rows, box_cols], 128B swizzle.
+// box_cols * elem_bytes must be 128 (one swizzle row).
+inline CUtensorMap make_tma_2d(const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_bytes,
+                               uint32_t box_rows, uint32_t box_cols, CUtensorMapDataType dtype, int elem_bytes) {
+  CUtensorMap m;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {row_stride_bytes};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  if (box_cols * elem_bytes != 128) throw std::runtime_error("TMA box inner extent must be 128 bytes");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (row_stride_bytes & 15))
+    throw std::runtime_error("TMA tensors need 16-byte aligned base and row stride");
+  CUresult r = tensor_map_encoder()(&m, dtype, 2, const_cast<void*>(base), dims, strides, box, estr,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled failed: " + std::to_string(int(r)));
+  return m;
+}
+
+}  // namespace nrl

@@ -1,0 +1,227 @@
+"""T2: every csrc/ kernel against the plain-PyTorch fp32 oracle (ops/reference.py).  Needs a B200."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from nanorlhf_b200.ops import reference as ref
+
+
+def _native():
+    from nanorlhf_b200.ops import native
+    native.load()
+    return native
+
+
+def _rel(a, b):
+    return ((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-12)).item()
+
+
+@pytest.mark.parametrize("M,N,K,bn", [(128, 256, 64, 256), (256, 512, 1536, 256), (2048, 2048, 1536, 0), (300, 1536, 8960, 0),
+                                       (6800, 17920, 1536, 0), (77, 136, 200, 128), (4096, 1536, 1536, 128)])
+def test_gemm_bf16(M, N, K, bn):
+    n = _native()
+    torch.manual_seed(0)
+    a = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
+    b = torch.randn(N, K, device="cuda", dtype=torch.bfloat16)
+    bias = torch.randn(N, device="cuda", dtype=torch.bfloat16)
+    out = n.gemm_bf16(a, b, bias, None, bn)
+    want = a.float() @ b.float().t() + bias.float()
+    assert _rel(out, want) < 1e-2
+    out2 = n.gemm_bf16(a, b)
+    assert _rel(out2, a.float() @ b.float().t()) < 1e-2
+
+
+def test_linear_autograd():
+    n = _native()
+    torch.manual_seed(0)
+    x = torch.randn(512, 256, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+    w = torch.randn(384, 256, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+    b = torch.randn(384, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+    y = n.linear(x, w, b)
+    g = torch.randn_like(y)
+    y.backward(g)
+    xr, wr, br = (t.detach().float().requires_grad_(True) for t in (x, w, b))
+    yr = xr @ wr.t() + br
+    yr.backward(g.float())
+    assert _rel(y, yr) < 1e-2 and _rel(x.grad, xr.grad) < 1e-2 and _rel(w.grad, wr.grad) < 1e-2 and _rel(b.grad, br.grad) < 1e-2
+
+
+@pytest.mark.parametrize("T,V,d,temp", [(300, 5000, 256, 0.9), (1000, 151936, 1536, 0.9), (129, 1024, 64, 1.0)])
+def test_lmhead_logprob(T, V, d, temp):
+    n = _native()
+    torch.manual_seed(0)
+    h = (torch.randn(T, d, device="cuda") * 1.0).bfloat16().requires_grad_(True)
+    w = (torch.randn(V, d, device="cuda") * 0.05).bfloat16().requires_grad_(True)
+    tgt = torch.randint(0, V, (T,), device="cuda")
+    logp, ent = n.lmhead_logprob(h, w, tgt, temp, True)
+    lp_ref, ent_ref, lse_ref = ref.lmhead_logprob(h.detach(), w.detach(), tgt, temp)
+    assert (logp - lp_ref).abs().max().item() < 2e-2
+    assert (ent - ent_ref).abs().max().item() < 2e-2
+    g = torch.randn(T, device="cuda")
+    logp.backward(g)
+    dh_ref, dw_ref = ref.lmhead_logprob_backward(h.detach(), w.detach(), tgt, lse_ref, g, temp, True)
+    assert _rel(h.grad, dh_ref) < 3e-2
+    assert _rel(w.grad, dw_ref) < 3e-2
+
+
+@pytest.mark.parametrize("rows,d", [(1000, 1536), (37, 3584), (5, 64)])
+def test_rmsnorm(rows, d):
+    n = _native()
+    torch.manual_seed(0)
+    x = torch.randn(rows, d, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+    w = (1 + 0.1 * torch.randn(d, device="cuda")).bfloat16().requires_grad_(True)
+    y = n.rmsnorm(x, w, 1e-6)
+    g = torch.randn_like(y)
+    y.backward(g)
+    xr, wr = x.detach().float().requires_grad_(True), w.detach().float().requires_grad_(True)
+    yr = ref.rmsnorm(xr, wr, 1e-6)
+    yr.backward(g.float())
+    assert _rel(y, yr) < 1e-2 and _rel(x.grad, xr.grad) < 2e-2 and _rel(w.grad, wr.grad) < 2e-2
+    res = torch.randn_like(x)
+    y2, r2 = n.add_rmsnorm(x.detach(), res, w.detach(), 1e-6)
+    yy, rr = ref.add_rmsnorm(x.detach(), res, w.detach(), 1e-6)
+    assert _rel(y2, yy) < 1e-2 and _rel(r2, rr) < 1e-2
+
+
+def test_rope_and_swiglu():
+    n = _native()
+    torch.manual_seed(0)
+    T, H, D = 333, 12, 128
+    x = torch.randn(T, H, D, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+    pos = torch.randint(0, 4000, (T,), device="cuda")
+    cos, sin = ref.rope_cos_sin(pos, D, 1e6)
+    y = n.apply_rope(x, cos, sin)
+    g = torch.randn_like(y)
+    y.backward(g)
+    xr = x.detach().float().requires_grad_(True)
+    yr = ref.apply_rope(xr, cos, sin)
+    yr.backward(g.float())
+    assert _rel(y, yr) < 1e-2 and _rel(x.grad, xr.grad) < 1e-2
+    gu = torch.randn(777, 2 * 8960, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+    o = n.swiglu(gu)
+    go = torch.randn_like(o)
+    o.backward(go)
+    gr = gu.detach().float().requires_grad_(True)
+    orf = ref.swiglu(gr)
+    orf.backward(go.float())
+    assert _rel(o, orf) < 1e-2 and _rel(gu.grad, gr.grad) < 1e-2
+
+
+@pytest.mark.parametrize("gamma,lam,with_values", [(1.0, 1.0, False), (0.99, 0.95, True), (1.0, 0.95, True)])
+def test_gae_scan(gamma, lam, with_values):
+    n = _native()
+    torch.manual_seed(0)
+    B, T = 37, 1500
+    r = torch.randn(B, T, device="cuda")
+    v = torch.randn(B, T, device="cuda") if with_values else None
+    adv, ret = n.gae_scan(r, v, gamma, lam)
+    if with_values:
+        a_ref, r_ref = ref.gae(r, v, gamma, lam)
+        assert torch.allclose(ret, r_ref, atol=2e-3, rtol=1e-3)
+    else:
+        a_ref = ref.discounted_suffix_sum(r, gamma * lam)
+    assert torch.allclose(adv, a_ref, atol=2e-3, rtol=1e-3)
+
+
+def test_policy_and_value_loss():
+    n = _native()
+    torch.manual_seed(0)
+    B, T = 4, 1500
+    new = (torch.randn(B, T, device="cuda") * 0.3 - 2).requires_grad_(True)
+    old = new.detach() + 0.3 * torch.randn(B, T, device="cuda")
+    refl = new.detach() + 0.2 * torch.randn(B, T, device="cuda")
+    adv = torch.randn(B, T, device="cuda")
+    mask = torch.rand(B, T, device="cuda") > 0.3
+    for rl, kc in ((None, 0.0), (refl, 0.05)):
+        new.grad = None
+        loss, st = n.policy_loss_token(new, old, adv, mask, 0.2, rl, kc)
+        loss.backward()
+        nr = new.detach().clone().requires_grad_(True)
+        lr, sr = ref.policy_loss_token(nr, old, adv, mask, 0.2, rl, kc)
+        lr.backward()
+        assert abs(loss.item() - lr.item()) < 1e-4
+        assert torch.allclose(new.grad, nr.grad, atol=1e-6, rtol=1e-3)
+        for k in sr:
+            assert abs(st[k].item() - sr[k].item()) < 1e-3, k
+    vp = torch.randn(B, T, device="cuda", requires_grad=True)
+    vo = vp.detach() + 0.3 * torch.randn(B, T, device="cuda")
+    R = torch.randn(B, T, device="cuda")
+    l, cf = n.value_loss(vp, vo, R, mask, 0.2)
+    l.backward()
+    vr = vp.detach().clone().requires_grad_(True)
+    l2, cf2 = ref.value_loss(vr, vo, R, mask, 0.2)
+    l2.backward()
+    assert abs(l.item() - l2.item()) < 1e-4 and abs(cf.item() - cf2.item()) < 1e-4
+    assert torch.allclose(vp.grad, vr.grad, atol=1e-6, rtol=1e-3)
+
+
+@pytest.mark.parametrize("state_dtype", [torch.float32, torch.bfloat16])
+def test_adamw_flat(state_dtype):
+    n = _native()
+    torch.manual_seed(0)
+    N = 1024 * 37
+    p = torch.randn(N, device="cuda").bfloat16()
+    g = torch.randn(N, device="cuda").bfloat16()
+    m = torch.zeros(N, device="cuda", dtype=state_dtype)
+    v = torch.zeros(N, device="cuda", dtype=state_dtype)
+    p2, m2, v2 = p.clone(), m.clone(), v.clone()
+    for step in (1, 2, 3):
+        n.adamw_flat(p, g, m, v, 1e-2, 0.9, 0.999, 1e-8, 0.01, step, 0.5)
+        ref.adamw_step_(p2, g, m2, v2, 1e-2, 0.9, 0.999, 1e-8, 0.01, step, grad_scale=0.5)
+    assert _rel(p, p2) < 1e-2 and _rel(m, m2) < 2e-2 and _rel(v, v2) < 2e-2
+
+
+def test_sampling_greedy_and_distribution():
+    n = _native()
+    torch.manual_seed(0)
+    V = 151936
+    logits = torch.randn(64, V, device="cuda").bfloat16()
+    tok = n.sample(logits, 0.0, 1.0, 1, 0)
+    assert torch.equal(tok.long(), logits.float().argmax(-1))
+    # peaked distribution over few tokens: empirical frequencies match the truncated softmax
+    V2 = 1024
+    base = torch.full((V2,), -20.0, device="cuda")
+    base[:8] = torch.tensor([3.0, 2.5, 2.0, 1.0, 0.5, 0.0, -1.0, -3.0], device="cuda")
+    S = 20000
+    lg = base[None].expand(S, V2).contiguous()
+    tok = n.sample(lg, 0.9, 0.95, 1234, 7)
+    tok2 = n.sample(lg, 0.9, 0.95, 1234, 7)
+    assert torch.equal(tok, tok2)                      # seed-reproducible
+    assert not torch.equal(tok, n.sample(lg, 0.9, 0.95, 1235, 7))
+    probs = torch.softmax(base / 0.9, -1)
+    sp, si = probs.sort(descending=True)
+    keep = (sp.cumsum(0) - sp) < 0.95
+    tp = torch.zeros_like(probs)
+    tp[si[keep]] = sp[keep]
+    tp = tp / tp.sum()
+    freq = torch.bincount(tok.long(), minlength=V2).float() / S
+    assert (freq - tp).abs().max().item() < 0.02
+    assert freq[(tp == 0)].sum().item() < 0.03
+
+
+@pytest.mark.parametrize("Hq,Hkv,splits", [(12, 2, 1), (28, 4, 1), (12, 2, 3)])
+def test_paged_decode(Hq, Hkv, splits):
+    n = _native()
+    torch.manual_seed(0)
+    S, D, bs, nblk = 33, 128, 16, 600
+    ctx = torch.randint(1, 250, (S,), device="cuda", dtype=torch.int32)
+    ctx[0], ctx[1] = 1, 16
+    maxb = int((ctx.max().item() + bs - 1) // bs)
+    perm = torch.randperm(nblk, device="cuda")[: S * maxb].view(S, maxb).to(torch.int32)
+    kc = torch.randn(nblk, Hkv, bs, D, device="cuda").bfloat16()
+    vc = torch.randn(nblk, Hkv, bs, D, device="cuda").bfloat16()
+    q = torch.randn(S, Hq, D, device="cuda").bfloat16()
+    out = n.paged_decode(q, kc, vc, perm, ctx, None, splits)
+    want = ref.paged_attention_decode(q, kc, vc, perm, ctx)
+    assert _rel(out, want) < 2e-2
+    # cache writer round trip
+    T = 50
+    k = torch.randn(T, Hkv, D, device="cuda").bfloat16()
+    v = torch.randn(T, Hkv, D, device="cuda").bfloat16()
+    slots = torch.randperm(nblk * bs, device="cuda")[:T].to(torch.int32)
+    n.kv_cache_write(k, v, kc, vc, slots)
+    blk, off = (slots // bs).long(), (slots % bs).long()
+    assert torch.equal(kc[blk, :, off], k) and torch.equal(vc[blk, :, off], v)
