@@ -46,17 +46,18 @@ NRL_DEVICE uint32_t swz(int r, int c) { return static_cast<uint32_t>(r * 256 + (
 // k, v: [T, Hkv, D] (row stride given) ; caches: [num_blocks, Hkv, kPage, D]; slot = block * kPage + offset
 __global__ void kv_cache_write_kernel(const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restrict__ v,
                                       long k_stride_t, long v_stride_t, __nv_bfloat16* __restrict__ k_cache,
-                                      __nv_bfloat16* __restrict__ v_cache, const int* __restrict__ slot_mapping, int T,
-                                      int Hkv) {
+                                      __nv_bfloat16* __restrict__ v_cache, const int* __restrict__ slot_mapping,
+                                      const int* __restrict__ src_index, int T, int Hkv) {
   const int vec_per_tok = Hkv * (kHeadDim / 8);
   const long total = static_cast<long>(T) * vec_per_tok;
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long>(gridDim.x) * blockDim.x) {
-    const int t = i / vec_per_tok;
+    const int pair = i / vec_per_tok;
     const int r = i % vec_per_tok;
+    const long t = src_index ? src_index[pair] : pair;
     const int h = r / (kHeadDim / 8);
     const int c = r % (kHeadDim / 8);
-    const int slot = slot_mapping[t];
+    const int slot = slot_mapping[pair];
     if (slot < 0) continue;
     const long dst = ((static_cast<long>(slot / kPage) * Hkv + h) * kPage + (slot % kPage)) * kHeadDim + c * 8;
     *reinterpret_cast<uint4*>(k_cache + dst) = *reinterpret_cast<const uint4*>(k + t * k_stride_t + h * kHeadDim + c * 8);
@@ -275,8 +276,8 @@ __global__ void decode_merge_splits_kernel(DecodeParams p) {
 using namespace nrl;
 
 extern "C" cudaError_t nrl_kv_cache_write(const void* k, const void* v, long k_stride_t, long v_stride_t, void* k_cache,
-                                          void* v_cache, const int* slot_mapping, int T, int Hkv, int head_dim,
-                                          int page, cudaStream_t s) {
+                                          void* v_cache, const int* slot_mapping, const int* src_index, int T, int Hkv,
+                                          int head_dim, int page, cudaStream_t s) {
   if (head_dim != kHeadDim || page != kPage) return cudaErrorInvalidValue;
   if (T == 0) return cudaSuccess;
   long total = static_cast<long>(T) * Hkv * (kHeadDim / 8);
@@ -284,7 +285,7 @@ extern "C" cudaError_t nrl_kv_cache_write(const void* k, const void* v, long k_s
   if (blocks > 148L * 8) blocks = 148L * 8;
   kv_cache_write_kernel<<<static_cast<int>(blocks), 256, 0, s>>>(
       static_cast<const __nv_bfloat16*>(k), static_cast<const __nv_bfloat16*>(v), k_stride_t, v_stride_t,
-      static_cast<__nv_bfloat16*>(k_cache), static_cast<__nv_bfloat16*>(v_cache), slot_mapping, T, Hkv);
+      static_cast<__nv_bfloat16*>(k_cache), static_cast<__nv_bfloat16*>(v_cache), slot_mapping, src_index, T, Hkv);
   return cudaGetLastError();
 }
 

@@ -270,7 +270,8 @@ void adamw_flat(torch::Tensor param, const torch::Tensor& grad, torch::Tensor m,
 
 // ---- sampler kernels ------------------------------------------------------------------------------
 torch::Tensor sample(const torch::Tensor& logits, double temperature, double top_p, int64_t seed, int64_t step,
-                     const c10::optional<torch::Tensor>& row_ids, c10::optional<torch::Tensor> out_opt) {
+                     const c10::optional<torch::Tensor>& row_ids, const c10::optional<torch::Tensor>& row_steps,
+                     c10::optional<torch::Tensor> out_opt) {
   TORCH_CHECK(logits.is_cuda() && logits.dim() == 2 && logits.stride(1) == 1);
   const bool bf16 = logits.scalar_type() == torch::kBFloat16;
   TORCH_CHECK(bf16 || logits.scalar_type() == torch::kFloat32);
@@ -279,20 +280,29 @@ torch::Tensor sample(const torch::Tensor& logits, double temperature, double top
   torch::Tensor out = out_opt.has_value() ? *out_opt : torch::empty({logits.size(0)}, logits.options().dtype(torch::kInt32));
   const int* rid = nullptr;
   if (row_ids.has_value()) rid = row_ids->data_ptr<int>();
+  const int* rst = nullptr;
+  if (row_steps.has_value()) rst = row_steps->data_ptr<int>();
   check(nrl_sample(logits.data_ptr(), bf16 ? 1 : 0, logits.stride(0), logits.size(0), logits.size(1),
                    static_cast<float>(temperature), static_cast<float>(top_p), static_cast<unsigned long long>(seed),
-                   static_cast<unsigned long long>(step), rid, out.data_ptr<int>(), cur_stream()), "sample");
+                   static_cast<unsigned long long>(step), rid, rst, out.data_ptr<int>(), cur_stream()), "sample");
   return out;
 }
 
 void kv_cache_write(const torch::Tensor& k, const torch::Tensor& v, torch::Tensor k_cache, torch::Tensor v_cache,
-                    const torch::Tensor& slot_mapping) {
+                    const torch::Tensor& slot_mapping, const c10::optional<torch::Tensor>& src_index) {
   TORCH_CHECK(k.dim() == 3 && v.dim() == 3 && k.stride(2) == 1 && k.stride(1) == k.size(2) && v.stride(2) == 1 && v.stride(1) == v.size(2));
   TORCH_CHECK(k_cache.dim() == 4 && k_cache.is_contiguous() && v_cache.is_contiguous());
-  TORCH_CHECK(slot_mapping.scalar_type() == torch::kInt32 && slot_mapping.numel() == k.size(0));
+  TORCH_CHECK(slot_mapping.scalar_type() == torch::kInt32 && slot_mapping.is_contiguous());
+  const int* src = nullptr;
+  if (src_index.has_value()) {
+    TORCH_CHECK(src_index->scalar_type() == torch::kInt32 && src_index->numel() == slot_mapping.numel());
+    src = src_index->data_ptr<int>();
+  } else {
+    TORCH_CHECK(slot_mapping.numel() == k.size(0));
+  }
   c10::cuda::CUDAGuard guard(k.device());
   check(nrl_kv_cache_write(k.data_ptr(), v.data_ptr(), k.stride(0), v.stride(0), k_cache.data_ptr(), v_cache.data_ptr(),
-                           slot_mapping.data_ptr<int>(), k.size(0), k.size(1), k.size(2), k_cache.size(2), cur_stream()),
+                           slot_mapping.data_ptr<int>(), src, slot_mapping.numel(), k.size(1), k.size(2), k_cache.size(2), cur_stream()),
         "kv_cache_write");
 }
 
@@ -339,8 +349,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("value_loss", &value_loss);
   m.def("adamw_flat", &adamw_flat);
   m.def("sample", &sample, py::arg("logits"), py::arg("temperature"), py::arg("top_p"), py::arg("seed"), py::arg("step"),
-        py::arg("row_ids") = py::none(), py::arg("out") = py::none());
-  m.def("kv_cache_write", &kv_cache_write);
+        py::arg("row_ids") = py::none(), py::arg("row_steps") = py::none(), py::arg("out") = py::none());
+  m.def("kv_cache_write", &kv_cache_write, py::arg("k"), py::arg("v"), py::arg("k_cache"), py::arg("v_cache"),
+        py::arg("slot_mapping"), py::arg("src_index") = py::none());
   m.def("paged_decode", &paged_decode, py::arg("q"), py::arg("k_cache"), py::arg("v_cache"), py::arg("block_tables"),
         py::arg("context_lens"), py::arg("scale"), py::arg("splits") = 1, py::arg("out") = py::none());
   nrl::bind_runtime(m);

@@ -34,12 +34,12 @@ cudaError_t nrl_adamw_flat(void* param, const void* grad, void* m, void* v, long
 
 cudaError_t nrl_sample(const void* logits, int is_bf16, long row_stride, int rows, int V, float temperature,
                        float top_p, unsigned long long seed, unsigned long long step, const int* row_ids,
-                       int* out_tokens, cudaStream_t s);
+                       const int* row_steps, int* out_tokens, cudaStream_t s);
 }
 
 extern "C" {
 cudaError_t nrl_kv_cache_write(const void* k, const void* v, long k_stride_t, long v_stride_t, void* k_cache,
-                               void* v_cache, const int* slot_mapping, int T, int Hkv, int head_dim, int page,
+                               void* v_cache, const int* slot_mapping, const int* src_index, int T, int Hkv, int head_dim, int page,
                                cudaStream_t s);
 cudaError_t nrl_paged_decode(const void* q, long q_stride_s, const void* k_cache, const void* v_cache,
                              const int* block_tables, const int* context_lens, void* out, float* part_o,

@@ -71,6 +71,7 @@ __global__ void __launch_bounds__(kSampThreads) sample_top_p_kernel(const T* __r
                                                                     int V, float inv_temp, float top_p,
                                                                     unsigned long long seed, unsigned long long step,
                                                                     const int* __restrict__ row_ids,
+                                                                    const int* __restrict__ row_steps,
                                                                     int* __restrict__ out_tokens) {
   __shared__ float red[32];
   __shared__ float hist[kBins];
@@ -194,7 +195,8 @@ __global__ void __launch_bounds__(kSampThreads) sample_top_p_kernel(const T* __r
     float u = 0.f;
     if (tid == 0) {
       curandStatePhilox4_32_10_t st;
-      curand_init(seed, static_cast<unsigned long long>(row_ids ? row_ids[row] : row), step, &st);
+      curand_init(seed, static_cast<unsigned long long>(row_ids ? row_ids[row] : row),
+                  step + (row_steps ? static_cast<unsigned long long>(row_steps[row]) : 0ull), &st);
       u = curand_uniform(&st) * total;              // (0, total]
     }
     u = __shfl_sync(0xffffffffu, u, 0);
@@ -290,7 +292,7 @@ using namespace nrl;
 
 extern "C" cudaError_t nrl_sample(const void* logits, int is_bf16, long row_stride, int rows, int V, float temperature,
                                   float top_p, unsigned long long seed, unsigned long long step, const int* row_ids,
-                                  int* out_tokens, cudaStream_t s) {
+                                  const int* row_steps, int* out_tokens, cudaStream_t s) {
   if (rows == 0) return cudaSuccess;
   if (temperature == 0.f) {
     if (is_bf16)
@@ -302,10 +304,10 @@ extern "C" cudaError_t nrl_sample(const void* logits, int is_bf16, long row_stri
     if (top_p >= 1.f) top_p = 2.f;     // keep everything
     if (is_bf16)
       sample_top_p_kernel<__nv_bfloat16><<<rows, kSampThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(logits), row_stride, V,
-                                                                       inv_t, top_p, seed, step, row_ids, out_tokens);
+                                                                       inv_t, top_p, seed, step, row_ids, row_steps, out_tokens);
     else
       sample_top_p_kernel<float><<<rows, kSampThreads, 0, s>>>(static_cast<const float*>(logits), row_stride, V, inv_t,
-                                                               top_p, seed, step, row_ids, out_tokens);
+                                                               top_p, seed, step, row_ids, row_steps, out_tokens);
   }
   return cudaGetLastError();
 }

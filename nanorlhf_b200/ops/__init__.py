@@ -20,7 +20,7 @@ _native = None
 _native_err = None
 
 
-def native():
+def _nat():
     """Return the loaded native extension module, raising a clear error if it is unavailable."""
     global _native, _native_err
     if _native is None and _native_err is None:
@@ -51,38 +51,38 @@ def backend_name(t: torch.Tensor) -> str:
 # ---- thin dispatchers (autograd-aware wrappers live in ops/native.py) -----------------------
 def rmsnorm(x, weight, eps):
     if use_native(x):
-        return native().rmsnorm(x, weight, eps)
+        return _nat().rmsnorm(x, weight, eps)
     return ref.rmsnorm(x, weight, eps)
 
 
 def add_rmsnorm(x, residual, weight, eps):
     if use_native(x):
-        return native().add_rmsnorm(x, residual, weight, eps)
+        return _nat().add_rmsnorm(x, residual, weight, eps)
     return ref.add_rmsnorm(x, residual, weight, eps)
 
 
 def apply_rope(x, cos, sin):
     if use_native(x):
-        return native().apply_rope(x, cos, sin)
+        return _nat().apply_rope(x, cos, sin)
     return ref.apply_rope(x, cos, sin)
 
 
 def swiglu(gate_up):
     if use_native(gate_up):
-        return native().swiglu(gate_up)
+        return _nat().swiglu(gate_up)
     return ref.swiglu(gate_up)
 
 
 def attention_varlen(q, k, v, cu_seqlens, max_seqlen=None, causal=True, scale=None):
     if use_native(q):
-        return native().attention_varlen(q, k, v, cu_seqlens, max_seqlen, causal, scale)
+        return _nat().attention_varlen(q, k, v, cu_seqlens, max_seqlen, causal, scale)
     return ref.attention_varlen(q, k, v, cu_seqlens, causal=causal, scale=scale)
 
 
 def lmhead_logprob(hidden, weight, targets, temperature=1.0, want_entropy=True):
     """Autograd-capable fused lm-head log-prob.  Returns (logp, entropy) both fp32 [T]."""
     if use_native(hidden):
-        return native().lmhead_logprob(hidden, weight, targets, temperature, want_entropy)
+        return _nat().lmhead_logprob(hidden, weight, targets, temperature, want_entropy)
     return _LmHeadLogprobTorch.apply(hidden, weight, targets, float(temperature), bool(want_entropy))
 
 
@@ -107,19 +107,19 @@ class _LmHeadLogprobTorch(torch.autograd.Function):
 
 def discounted_suffix_sum(rewards, gamma=1.0):
     if use_native(rewards):
-        return native().gae_scan(rewards, None, gamma, 1.0)[0]
+        return _nat().gae_scan(rewards, None, gamma, 1.0)[0]
     return ref.discounted_suffix_sum(rewards, gamma)
 
 
 def gae(rewards, values, gamma, lam):
     if use_native(rewards):
-        return native().gae_scan(rewards, values, gamma, lam)
+        return _nat().gae_scan(rewards, values, gamma, lam)
     return ref.gae(rewards, values, gamma, lam)
 
 
 def policy_loss_token(new_logp, old_logp, adv, mask, cliprange, ref_logp=None, kl_coef=0.0):
     if use_native(new_logp):
-        return native().policy_loss_token(new_logp, old_logp, adv, mask, cliprange, ref_logp, kl_coef)
+        return _nat().policy_loss_token(new_logp, old_logp, adv, mask, cliprange, ref_logp, kl_coef)
     return ref.policy_loss_token(new_logp, old_logp, adv, mask, cliprange, ref_logp, kl_coef)
 
 
@@ -129,5 +129,5 @@ nll_loss = ref.nll_loss
 
 def value_loss(vpred, values_old, returns, mask, cliprange_value):
     if use_native(vpred):
-        return native().value_loss(vpred, values_old, returns, mask, cliprange_value)
+        return _nat().value_loss(vpred, values_old, returns, mask, cliprange_value)
     return ref.value_loss(vpred, values_old, returns, mask, cliprange_value)

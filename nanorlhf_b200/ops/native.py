@@ -291,14 +291,14 @@ def adamw_flat(param, grad, m, v, lr, beta1, beta2, eps, wd, step, scale=1.0):
 # --------------------------------------------------------------------------------------------
 # sampler kernels
 # --------------------------------------------------------------------------------------------
-def sample(logits, temperature, top_p, seed, step, row_ids=None, out=None):
+def sample(logits, temperature, top_p, seed, step, row_ids=None, row_steps=None, out=None):
     _count()
-    return ext().sample(logits, float(temperature), float(top_p), int(seed), int(step), row_ids, out)
+    return ext().sample(logits, float(temperature), float(top_p), int(seed), int(step), row_ids, row_steps, out)
 
 
-def kv_cache_write(k, v, k_cache, v_cache, slot_mapping):
+def kv_cache_write(k, v, k_cache, v_cache, slot_mapping, src_index=None):
     _count()
-    ext().kv_cache_write(k, v, k_cache, v_cache, slot_mapping)
+    ext().kv_cache_write(k, v, k_cache, v_cache, slot_mapping, src_index)
 
 
 def paged_decode(q, k_cache, v_cache, block_tables, context_lens, scale=None, splits=1, out=None):

@@ -140,7 +140,7 @@ class FusedAdamW(torch.optim.Optimizer):
                 else:
                     scale = self.grad_scale
                 if ops.use_native(f.param):
-                    ops.native().adamw_flat(f.param, f.grad, f.exp_avg, f.exp_avg_sq, scale=scale, **hp)
+                    ops._nat().adamw_flat(f.param, f.grad, f.exp_avg, f.exp_avg_sq, scale=scale, **hp)
                 else:
                     ref.adamw_step_(f.param, f.grad, f.exp_avg, f.exp_avg_sq, hp["lr"], b1, b2, hp["eps"], hp["wd"],
                                     self._step, grad_scale=scale)

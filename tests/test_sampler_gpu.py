@@ -1,0 +1,56 @@
+"""Native sampler vs the PyTorch reference sampler (token-exact at temperature 0)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _models():
+    from nanorlhf_b200.models.lora import LoraConfig, get_peft_model
+    from nanorlhf_b200.models.qwen2 import Qwen2Config, Qwen2ForCausalLM
+    cfg = Qwen2Config(vocab_size=2048, hidden_size=256, intermediate_size=512, num_hidden_layers=3,
+                      num_attention_heads=4, num_key_value_heads=2, head_dim=128, tie_word_embeddings=True)
+    m = Qwen2ForCausalLM.from_config(cfg, torch.bfloat16, "cuda", seed=3)
+    m = get_peft_model(m, LoraConfig(r=8, lora_alpha=16, modules_to_save=None))
+    with torch.no_grad():
+        for mod in m.modules():
+            if hasattr(mod, "lora_B"):
+                mod.lora_B.weight.normal_(0, 0.02)
+    return m
+
+
+def test_greedy_matches_torch_sampler():
+    from nanorlhf_b200.sampler.native_sampler import NativeSampler
+    from nanorlhf_b200.sampler.torch_sampler import torch_generate
+    m = _models()
+    g = torch.Generator().manual_seed(0)
+    prompts = [torch.randint(0, 2000, (int(L),), generator=g).tolist() for L in (5, 16, 17, 33, 64, 9, 31, 48)]
+    eng = NativeSampler(m, kv_cache_gb=1.0, sync_every=8)
+    eng.sync_weights()
+    out = eng.generate(prompts, 2, 0.0, 1.0, 24, None, 2047, 1)
+    want = torch_generate(m, prompts, 2, 0.0, 1.0, 24, None, 2047, 1)
+    agree = (out == want).float().mean().item()
+    # bf16 kernels differ in rounding from the fp32-softmax reference: demand near-exact agreement
+    first_tok = (out[:, 0] == want[:, 0]).float().mean().item()
+    assert first_tok == 1.0, (out[:, :4], want[:, :4])
+    assert agree > 0.9, agree
+
+
+def test_sampling_is_seeded_and_eos_stops():
+    from nanorlhf_b200.sampler.native_sampler import NativeSampler
+    m = _models()
+    prompts = [[1, 2, 3, 4, 5, 6, 7], [8, 9, 10]]
+    eng = NativeSampler(m, kv_cache_gb=1.0, sync_every=8)
+    eng.sync_weights()
+    a = eng.generate(prompts, 4, 0.9, 0.95, 20, None, 2047, 11)
+    b = eng.generate(prompts, 4, 0.9, 0.95, 20, None, 2047, 11)
+    c = eng.generate(prompts, 4, 0.9, 0.95, 20, None, 2047, 12)
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    assert a.shape == (8, 20) and (a != 2047).all()
+    # pick the most frequent first token as "eos": rows that emit it must be padded afterwards
+    eos = int(a[:, 3].mode().values)
+    d = eng.generate(prompts, 4, 0.9, 0.95, 20, eos, 2047, 11)
+    for row in d.tolist():
+        if eos in row:
+            i = row.index(eos)
+            assert all(t == 2047 for t in row[i + 1:])
