@@ -1,0 +1,299 @@
+"""Rule-based math reward: boxed-answer extraction + answer equivalence with a *working* timeout.
+
+Reference: the r1-v0 example rewards 1/0 by comparing the ``\\boxed{}`` content of the response with the
+MetaMathQA "The answer is: X" ground truth through ``iscorrect`` (/root/reference/examples/r1-v0/
+grpo_r1.py:194-224,250-273), backed by 2.4 kLoC of vendored graders (``utils/toolkit_for_MATH/
+latex_answer_check.py``, ``utils/eval/eval_script.py``, ``utils/eval/eval_utils.py``,
+``utils/data_processing/answer_extraction.py``).  In the shipped reference the symbolic graders are never
+reached: every comparison is forked into a fresh process with a 15 ms join timeout and a mismatched
+argument list, so the effective rule is a whitespace-stripped exact string match.
+
+This module implements the *intended* behaviour, re-derived from the description of those graders:
+  normalise (MATH-style ``strip_string``) -> exact match -> numeric match (floats, fractions, percent,
+  thousands separators) -> set/interval/tuple element-wise match -> symbolic equivalence with sympy,
+run inside a persistent worker pool with a real per-comparison timeout; ``match="exact"`` reproduces
+the shipped behaviour.
+"""
+from __future__ import annotations
+
+import math
+import multiprocessing as mp
+import re
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+# --------------------------------------------------------------------------------------------------
+# extraction
+# --------------------------------------------------------------------------------------------------
+def get_boxed(text: str) -> Optional[str]:
+    """Content of the last ``\\boxed{...}`` / ``\\fbox{...}`` (brace-matched); None when absent."""
+    idx = max(text.rfind("\\boxed"), text.rfind("\\fbox"))
+    if idx < 0:
+        return None
+    i = text.find("{", idx)
+    if i < 0:
+        # "\boxed 5" form
+        m = re.match(r"\\boxed\s+([^\s$]+)", text[idx:])
+        return m.group(1) if m else None
+    depth, j = 0, i
+    while j < len(text):
+        if text[j] == "{":
+            depth += 1
+        elif text[j] == "}":
+            depth -= 1
+            if depth == 0:
+                return text[i + 1:j]
+        j += 1
+    return None
+
+
+def extract_answer_is(text: str) -> Optional[str]:
+    """MetaMathQA ground truth: the text after the last 'The answer is: '."""
+    m = list(re.finditer(r"[Tt]he answer is:?\s*", text))
+    if not m:
+        return None
+    return text[m[-1].end():].strip().rstrip(".").strip()
+
+
+# --------------------------------------------------------------------------------------------------
+# normalisation (MATH "strip_string" family)
+# --------------------------------------------------------------------------------------------------
+_UNITS = ["degrees", "degree", "cm", "centimeters", "meters", "meter", "inches", "inch", "feet", "foot", "units", "unit",
+          "square", "cents", "cent", "dollars", "dollar", "mph", "hours", "hour", "minutes", "minute", "seconds",
+          "second", "days", "day", "years", "year", "pounds", "pound", "kg", "grams", "gram", "miles", "mile"]
+
+
+def _fix_fracs(s: str) -> str:
+    # \frac12 -> \frac{1}{2}, \frac1{2} -> \frac{1}{2}
+    out, i = "", 0
+    while i < len(s):
+        if s.startswith("\\frac", i):
+            j = i + 5
+            if j < len(s) and s[j] != "{":
+                if j + 1 < len(s) and s[j + 1] != "{":
+                    out += "\\frac{" + s[j] + "}{" + s[j + 1] + "}"
+                    i = j + 2
+                    continue
+                if j + 1 < len(s):
+                    out += "\\frac{" + s[j] + "}"
+                    i = j + 1
+                    continue
+        out += s[i]
+        i += 1
+    return out
+
+
+def _fix_a_slash_b(s: str) -> str:
+    m = re.fullmatch(r"(-?\d+)/(\d+)", s)
+    return f"\\frac{{{m.group(1)}}}{{{m.group(2)}}}" if m else s
+
+
+def _fix_sqrt(s: str) -> str:
+    return re.sub(r"\\sqrt(\w)", r"\\sqrt{\1}", s)
+
+
+def strip_string(s: str) -> str:
+    s = str(s).strip()
+    s = s.replace("\n", "").replace("\\!", "").replace("\\\\", "\\")
+    s = s.replace("tfrac", "frac").replace("dfrac", "frac")
+    s = s.replace("\\left", "").replace("\\right", "")
+    s = s.replace("^{\\circ}", "").replace("^\\circ", "").replace("°", "")
+    s = s.replace("\\$", "").replace("$", "")
+    s = re.sub(r"\\text\{\s*([^}]*)\}", r"\1", s)
+    s = re.sub(r"\\mbox\{\s*([^}]*)\}", r"\1", s)
+    for u in _UNITS:
+        s = re.sub(rf"(?<=[\d\s}}]){u}\b", "", s)
+    s = s.replace("\\%", "").replace("%", "")
+    s = s.replace(" .", " 0.").replace("{.", "{0.")
+    if s.startswith("."):
+        s = "0" + s
+    if len(s.split("=")) == 2 and len(s.split("=")[0]) <= 2:
+        s = s.split("=")[1]
+    s = _fix_sqrt(s)
+    s = s.replace(" ", "")
+    s = _fix_fracs(s)
+    if s == "0.5":
+        s = "\\frac{1}{2}"
+    s = _fix_a_slash_b(s)
+    s = re.sub(r"(\d),(?=\d{3}(\D|$))", r"\1", s)          # 1,000 -> 1000
+    s = s.rstrip(".")
+    return s
+
+
+# --------------------------------------------------------------------------------------------------
+# numeric / symbolic comparison
+# --------------------------------------------------------------------------------------------------
+def _to_float(s: str) -> Optional[float]:
+    s = s.replace(",", "")
+    m = re.fullmatch(r"\\frac\{(-?[\d.]+)\}\{(-?[\d.]+)\}", s)
+    try:
+        if m:
+            return float(m.group(1)) / float(m.group(2))
+        m = re.fullmatch(r"(-?)\\frac\{(-?[\d.]+)\}\{(-?[\d.]+)\}", s)
+        if m:
+            return (-1.0 if m.group(1) else 1.0) * float(m.group(2)) / float(m.group(3))
+        return float(s)
+    except (ValueError, ZeroDivisionError):
+        return None
+
+
+def numeric_equal(a: float, b: float, rel_tol: float = 1e-4) -> bool:
+    return math.isclose(a, b, rel_tol=rel_tol, abs_tol=1e-9)
+
+
+from ._sym_worker import latex_to_expr_text, symbolic_equal_impl as _symbolic_equal_impl, warm as _warm  # noqa: E402
+
+
+_POOL = None
+
+
+def _pool():
+    global _POOL
+    if _POOL is None:
+        ctx = mp.get_context("spawn")
+        _POOL = ctx.Pool(2, maxtasksperchild=500)
+        try:                      # pay the interpreter + sympy import once, outside any per-answer timeout
+            _POOL.apply_async(_warm).get(120)
+        except Exception:
+            pass
+    return _POOL
+
+
+def shutdown_pool():
+    global _POOL
+    if _POOL is not None:
+        _POOL.terminate()
+        _POOL = None
+
+
+def symbolic_equal(a: str, b: str, timeout_s: float = 3.0) -> bool:
+    """sympy equivalence in a persistent worker with a real timeout (a hung simplify kills the worker)."""
+    global _POOL
+    try:
+        return bool(_pool().apply_async(_symbolic_equal_impl, (a, b)).get(timeout_s))
+    except mp.TimeoutError:
+        shutdown_pool()         # the stuck worker is terminated; a fresh pool is built lazily
+        return False
+    except Exception:
+        return False
+
+
+def _split_elements(s: str) -> Optional[List[str]]:
+    if len(s) >= 2 and s[0] in "([{" and s[-1] in ")]}" and "," in s:
+        depth, cur, parts = 0, "", []
+        for ch in s[1:-1]:
+            if ch in "([{":
+                depth += 1
+            elif ch in ")]}":
+                depth -= 1
+            if ch == "," and depth == 0:
+                parts.append(cur)
+                cur = ""
+            else:
+                cur += ch
+        parts.append(cur)
+        return parts
+    return None
+
+
+def is_equiv(pred: str, gt: str, use_sympy: bool = True, timeout_s: float = 3.0) -> bool:
+    if pred is None or gt is None:
+        return False
+    a, b = strip_string(pred), strip_string(gt)
+    if a == b:
+        return True
+    if a.lower() == b.lower() and not any(c.isdigit() for c in a):
+        return True
+    fa, fb = _to_float(a), _to_float(b)
+    if fa is not None and fb is not None:
+        return numeric_equal(fa, fb) or numeric_equal(fa, fb / 100) or numeric_equal(fa / 100, fb)
+    if "\\cup" in a or "\\cup" in b:
+        pa, pb = a.split("\\cup"), b.split("\\cup")
+        return len(pa) == len(pb) and all(is_equiv(x, y, use_sympy, timeout_s) for x, y in zip(pa, pb))
+    ea, eb = _split_elements(a), _split_elements(b)
+    if ea is not None and eb is not None:
+        return (len(ea) == len(eb) and a[0] == b[0] and a[-1] == b[-1]
+                and all(is_equiv(x, y, use_sympy, timeout_s) for x, y in zip(ea, eb)))
+    if use_sympy and len(a) < 200 and len(b) < 200:
+        return symbolic_equal(a, b, timeout_s)
+    return False
+
+
+def iscorrect(answer: Optional[str], ground_truth: Optional[str], match: str = "equiv", timeout_s: float = 3.0) -> bool:
+    """``match='exact'`` = the shipped reference's effective rule (whitespace-stripped string equality)."""
+    if answer is None or ground_truth is None:
+        return False
+    if "".join(answer.split()) == "".join(ground_truth.split()):
+        return True
+    if match == "exact":
+        return False
+    return is_equiv(answer, ground_truth, True, timeout_s)
+
+
+# --------------------------------------------------------------------------------------------------
+# reward / accuracy callbacks
+# --------------------------------------------------------------------------------------------------
+R1_QUESTION_RE = re.compile(r"# Question:\n(.*?)\nPlease reason step by step", re.S)
+
+
+class RuleMathReward:
+    """``reward_func(pmt_and_responses, responses_ids, tokenizer) -> FloatTensor`` (grpo_r1.py:250-273)."""
+
+    def __init__(self, answers: Dict[str, str], match: str = "equiv", timeout_s: float = 3.0,
+                 question_re: re.Pattern = R1_QUESTION_RE, answer_marker: str = "# Answer:\n"):
+        self.answers, self.match, self.timeout_s = answers, match, timeout_s
+        self.question_re, self.answer_marker = question_re, answer_marker
+
+    def question_of(self, text: str) -> Optional[str]:
+        m = self.question_re.search(text)
+        return m.group(1) if m else None
+
+    def __call__(self, pmt_and_responses: Sequence[str], responses_ids=None, tokenizer=None) -> torch.Tensor:
+        eos = tokenizer.eos_token if (tokenizer is not None and not isinstance(tokenizer, str)) else (tokenizer or responses_ids)
+        out = torch.zeros(len(pmt_and_responses))
+        for i, text in enumerate(pmt_and_responses):
+            q = self.question_of(text)
+            gt = self.answers.get(q) if q is not None else None
+            k = text.rfind(self.answer_marker)
+            resp = text[k + len(self.answer_marker):] if k >= 0 else text
+            if isinstance(eos, str) and eos and eos in resp:
+                resp = resp[:resp.find(eos)]
+            out[i] = 1.0 if iscorrect(get_boxed(resp), gt, self.match, self.timeout_s) else 0.0
+        return out
+
+
+def make_accuracy_func(problems: Sequence[Dict[str, str]], tokenizer, template: str, max_tokens: int = 2048,
+                       match: str = "equiv"):
+    """``accuracy_func(model, args) -> float``: greedy (T=0, seed 42) decode of ``problems`` on the resident
+    sampler, accuracy by ``iscorrect`` (reference: MATH-500 probe, grpo_r1.py:276-341)."""
+    from ..sampler.engine import generate
+
+    def accuracy_func(model, args) -> float:
+        prompts = [tokenizer(template.replace("QUESTION", p["problem"]), padding=False)["input_ids"] for p in problems]
+        out = generate(1, model, tokenizer, prompts, 0.0, min(max_tokens, args.response_length), top_p=1.0, seed=42,
+                       backend=args.sampler, rollout_dtype=args.rollout_dtype)
+        texts = tokenizer.batch_decode(out)
+        good, lens = 0, []
+        for p, t in zip(problems, texts):
+            t = t.split(tokenizer.eos_token)[0].replace(tokenizer.pad_token, "")
+            lens.append(len(t))
+            good += int(iscorrect(get_boxed(t), p["answer"], match))
+        accuracy_func.last_mean_response_chars = sum(lens) / max(len(lens), 1)
+        return good / max(len(problems), 1)
+
+    return accuracy_func
+
+
+def synthetic_arithmetic_problems(n: int, seed: int = 0) -> List[Dict[str, str]]:
+    """Offline stand-in for MetaMathQA / MATH-500: two-operand arithmetic with exact answers."""
+    import random
+    rng = random.Random(seed)
+    out = []
+    for _ in range(n):
+        a, b = rng.randint(2, 99), rng.randint(2, 99)
+        op = rng.choice("+-*")
+        ans = {"+": a + b, "-": a - b, "*": a * b}[op]
+        q = f"What is {a} {op} {b}?"
+        out.append({"query": q, "problem": q, "response": f"... The answer is: {ans}", "answer": str(ans)})
+    return out

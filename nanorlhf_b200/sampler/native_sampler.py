@@ -205,7 +205,7 @@ class NativeSampler:
     # ------------------------------------------------------------------------------------------
     # decode
     # ------------------------------------------------------------------------------------------
-    def _alloc_state(self, S: int, max_blocks: int, max_tokens: int):
+    def _alloc_state(self, S: int, max_blocks: int, max_tokens: int, pad_id: int = 0):
         dev = self.device
         i32 = dict(dtype=torch.int32, device=dev)
         return {
@@ -213,7 +213,7 @@ class NativeSampler:
             "ctx_lens": torch.ones(S, **i32), "block_tables": torch.zeros(S, max_blocks, **i32),
             "slot": torch.zeros(S, **i32), "finished": torch.ones(S, dtype=torch.bool, device=dev),
             "gen_count": torch.zeros(S, **i32), "row_ids": torch.zeros(S, **i32),
-            "out": torch.zeros(S, max_tokens + 1, dtype=torch.int32, device=dev),
+            "out": torch.full((S, max_tokens + 1), pad_id, dtype=torch.int32, device=dev),
             "rows": torch.arange(S, device=dev), "splits": 1,
         }
 
@@ -267,8 +267,10 @@ class NativeSampler:
             for k, v in snap.items():
                 st[k].copy_(v)
             g = torch.cuda.CUDAGraph()
+            n0 = native.launches()
             with torch.cuda.graph(g):
                 self._decode_step(st, temperature, top_p, seed, eos_id, pad_id, max_tokens)
+            self._kernels_per_step = native.launches() - n0
             for k, v in snap.items():
                 st[k].copy_(v)
             # keep at most a handful of graphs alive
@@ -278,6 +280,7 @@ class NativeSampler:
         g = entry[0]
         for _ in range(steps):
             g.replay()
+        native._count(steps * getattr(self, "_kernels_per_step", 0))
         self.stats["graph_replays"] += steps
 
     # ------------------------------------------------------------------------------------------
@@ -332,7 +335,7 @@ class NativeSampler:
                         new_running += sched.group_seqs(g)
                 S_real = len(new_running)
                 S = max(128, (S_real + 127) // 128 * 128) if self.use_cuda_graph else S_real
-                st = self._alloc_state(S, per_seq_blocks, max_tokens)
+                st = self._alloc_state(S, per_seq_blocks, max_tokens, pad_id)
                 st["block_tables"].fill_(scratch_block)
                 bt = torch.full((S_real, per_seq_blocks), scratch_block, dtype=torch.int32)
                 for r, sid in enumerate(new_running):

@@ -140,6 +140,7 @@ class RLTrainer:
                                    args.watchdog_timeout_s, enable_watchdog=self.comm.world_size > 1)
         self.last_completions = None
         self._resumed = False
+        self.io_bytes = {"h2d": 0, "d2h": 0}           # host<->device traffic of the public step API
         if self.comm.is_main:
             os.makedirs(args.output_dir, exist_ok=True)
 
@@ -315,7 +316,11 @@ class RLTrainer:
         pad = self.tokenizer.pad_token_id
         t_start = time.time()
         self.state.episode += a.batch_size
-        queries = data["input_ids"].to(dev)
+        q_host = data["input_ids"]
+        if dev.type == "cuda":
+            q_host = q_host.pin_memory()                 # per-step inputs go pinned-host -> device
+        queries = q_host.to(dev, non_blocking=True)
+        self.io_bytes["h2d"] += q_host.numel() * q_host.element_size()
 
         with torch.no_grad():
             with self._phase("offload", update):
@@ -367,6 +372,7 @@ class RLTrainer:
         batch.update(advantages=adv, returns=returns, context_length=q.shape[1])
         with self._phase("train", update):
             stats = self.optimise(batch)
+        self._bump_policy_version()
 
         with torch.no_grad():
             metrics = self.assemble_metrics(stats, roll)
@@ -385,6 +391,12 @@ class RLTrainer:
 
     def post_score(self, queries, rollout, scores):
         return rollout
+
+    def _bump_policy_version(self):
+        """Tell the resident sampler that the policy weights changed (it re-merges LoRA lazily)."""
+        m = self.policy
+        m = getattr(m, "base_model", m) if hasattr(m, "peft_config") else m
+        m._nrl_version = getattr(m, "_nrl_version", 0) + 1
 
     # ---- phase 6 ------------------------------------------------------------------------------
     def optimise(self, batch) -> Dict[str, torch.Tensor]:
@@ -430,29 +442,37 @@ class RLTrainer:
     def assemble_metrics(self, stats, roll) -> Dict[str, float]:
         a = self.args
         inc = a.stats_include_padding
-        local = {
-            "objective/kl_old": float(self.kl_metric(stats, roll)),
-            "objective/entropy_old": float(roll["mean_entropy"]),
-            "objective/non_score_reward_old": float(roll["non_score"]) if self.kl_in_reward else 0.0,
-            "eval_objective/rlhf_reward_old": float(roll["rlhf_reward"]),
-            "eval_objective/scores_old": float(roll["scores"]),
-            "loss/policy_avg_new": float(stats["pg_loss"].mean()),
-            "policy/entropy_avg_new": float(stats["entropy"].mean()),
+        dev_vals = {
+            "objective/kl_old": self.kl_metric(stats, roll),
+            "objective/entropy_old": roll["mean_entropy"],
+            "objective/non_score_reward_old": roll["non_score"] if self.kl_in_reward else torch.zeros((), device=self.device),
+            "eval_objective/rlhf_reward_old": roll["rlhf_reward"],
+            "eval_objective/scores_old": roll["scores"],
+            "loss/policy_avg_new": stats["pg_loss"].mean(),
+            "policy/entropy_avg_new": stats["entropy"].mean(),
+            "_num_eos": roll["num_eos"].float(),
         }
         if self.logs_policy_ratio_stats:
-            local["policy/approxkl_avg_new"] = float(stats["approxkl_all" if inc else "approxkl_masked"].mean())
-            local["policy/clipfrac_avg_new"] = float(stats["clipfrac"].mean())
-            local["val/ratio_new"] = float(stats["ratio_mean_all" if inc else "ratio_mean_masked"].mean())
+            dev_vals["policy/approxkl_avg_new"] = stats["approxkl_all" if inc else "approxkl_masked"].mean()
+            dev_vals["policy/clipfrac_avg_new"] = stats["clipfrac"].mean()
+            dev_vals["val/ratio_new"] = stats["ratio_mean_all" if inc else "ratio_mean_masked"].mean()
         if self.uses_value_model:
-            local["loss/value_avg_new"] = float(stats["vf_loss"].mean())
-            local["val/clipfrac_avg_new"] = float(stats["vf_clipfrac"].mean())
+            dev_vals["loss/value_avg_new"] = stats["vf_loss"].mean()
+            dev_vals["val/clipfrac_avg_new"] = stats["vf_clipfrac"].mean()
+        keys = list(dev_vals)
+        # ONE device -> host read for the whole update's metrics
+        host = torch.stack([dev_vals[k].float().reshape(()) for k in keys]).cpu()
+        self.io_bytes["d2h"] += host.numel() * host.element_size()
+        local = {k: float(v) for k, v in zip(keys, host.tolist())}
+        num_eos = int(local.pop("_num_eos"))
+        if self.uses_value_model:
             local["eval_accuracy_new"] = 0.0
         out = self.comm.reduce_scalars(local, "mean")                     # ONE packed all-reduce (K23)
         if self.logs_policy_ratio_stats:
             r = stats["ratio_mean_all" if inc else "ratio_mean_masked"].reshape(-1)
             allr = self.comm.all_gather_cat(r)
             out["val/ratio_var_new"] = float(allr.var()) if allr.numel() > 1 else 0.0
-        out["val/num_eos_tokens_old"] = int(roll["num_eos"])
+        out["val/num_eos_tokens_old"] = num_eos
         return out
 
     def kl_metric(self, stats, roll):

@@ -1,0 +1,60 @@
+import pytest
+import torch
+
+from nanorlhf_b200.utils import (INVALID_LOGPROB, exact_div, first_true_indices, masked_mean, masked_var, masked_whiten,
+                                 response_masks, scatter_terminal_reward, truncate_response)
+from nanorlhf_b200.utils.schedules import get_scheduler
+
+
+def test_masked_mean_and_whiten():
+    torch.manual_seed(0)
+    x = torch.randn(4, 9)
+    m = torch.rand(4, 9) > 0.4
+    sel = x[m]
+    assert torch.allclose(masked_mean(x, m), sel.mean())
+    assert torch.allclose(masked_var(x, m), sel.var(unbiased=True), atol=1e-6)
+    w = masked_whiten(x, m)
+    assert abs(w[m].mean().item()) < 1e-5 and abs(w[m].var(unbiased=True).item() - 1) < 1e-3
+    w2 = masked_whiten(x, m, shift_mean=False)
+    assert torch.allclose(w2[m].mean(), sel.mean(), atol=1e-5)
+
+
+def test_first_true_and_truncate():
+    b = torch.tensor([[False, True, True], [False, False, False]])
+    assert first_true_indices(b).tolist() == [1, 3]
+    r = torch.tensor([[5, 9, 7, 9, 3], [1, 2, 3, 4, 5]])
+    t = truncate_response(9, 0, r)
+    assert t.tolist() == [[5, 9, 0, 0, 0], [1, 2, 3, 4, 5]]
+
+
+def test_masks_and_terminal_reward():
+    pad = 0
+    post = torch.tensor([[4, 4, 9, 0, 0], [4, 4, 4, 4, 4], [9, 0, 0, 0, 0]])
+    seq_len, pm, pm1 = response_masks(post, pad)
+    assert seq_len.tolist() == [2, 4, 0]
+    assert pm[0].tolist() == [False, False, False, True, True]
+    assert pm1[0].tolist() == [False, False, False, False, True]
+    assert not pm[1].any()
+    rew = scatter_terminal_reward(torch.zeros(3, 5), torch.tensor([1.0, 2.0, 3.0]), seq_len)
+    # actual_end = seq_len+1 when it fits, else seq_len
+    assert rew[0].tolist() == [0, 0, 0, 1, 0] and rew[1].tolist() == [0, 0, 0, 0, 2] and rew[2].tolist() == [0, 3, 0, 0, 0]
+    assert INVALID_LOGPROB == 1.0
+
+
+def test_exact_div():
+    assert exact_div(12, 4) == 3
+    with pytest.raises(ValueError):
+        exact_div(10, 4, "nope")
+
+
+def test_cosine_with_min_lr():
+    p = torch.nn.Parameter(torch.zeros(1))
+    opt = torch.optim.SGD([p], lr=1.0)
+    s = get_scheduler("cosine_with_min_lr", opt, 0, 10, {"min_lr_rate": 0.1})
+    lrs = []
+    for _ in range(10):
+        lrs.append(opt.param_groups[0]["lr"])
+        opt.step()
+        s.step()
+    assert lrs[0] == 1.0 and all(a >= b for a, b in zip(lrs, lrs[1:]))
+    assert abs(opt.param_groups[0]["lr"] - 0.1) < 1e-6
