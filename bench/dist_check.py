@@ -1,0 +1,143 @@
+"""Multi-GPU check + timing of the fused communication kernels (run under torchrun, one rank per GPU).
+
+  torchrun --nproc-per-node N --master-addr 127.0.0.1 bench/dist_check.py [--numel 540000000]
+
+1. fused in-place all-reduce (P2P) == dist.all_reduce (bf16 tolerance)
+2. fused all-reduce + AdamW (P2P and, when the NVLS multicast object exists, multimem) ==
+   dist.all_reduce + reference AdamW on every rank, and parameters identical across ranks
+3. device-timed (CUDA events, max over ranks) fused K-AR vs NCCL all-reduce + local fused AdamW
+Writes gpurun_out/dist_check_<N>.json (rank 0).
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from nanorlhf_b200.ops import native, reference as ref  # noqa: E402
+from nanorlhf_b200.parallel.comm import Comm  # noqa: E402
+from nanorlhf_b200.parallel.fused_allreduce import FusedAllReduceAdam  # noqa: E402
+
+
+def timed(fn, iters, comm):
+    for _ in range(3):
+        fn()
+    comm.barrier()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(iters):
+        fn()
+    e.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([s.elapsed_time(e) / iters], device="cuda", dtype=torch.float64)
+    comm.all_reduce_(t, "max")
+    return float(t)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--numel", type=int, default=540_672_000)      # ~LoRA r64 + embed + lm_head of Qwen2.5-1.5B
+    ap.add_argument("--iters", type=int, default=10)
+    args = ap.parse_args()
+    comm = Comm.from_env()
+    dev, W, R = comm.device, comm.world_size, comm.rank
+    native.load()
+    res = {"world": W, "numel": args.numel}
+    fa = FusedAllReduceAdam(comm)
+
+    # ---- 1. correctness on a small buffer --------------------------------------------------------------
+    n = 1024 * 64 * W
+    torch.manual_seed(100 + R)
+    g_sym = fa.alloc(n, torch.bfloat16, dev)
+    p_sym = fa.alloc(n, torch.bfloat16, dev)
+    g0 = torch.randn(n, device=dev).bfloat16()
+    torch.manual_seed(7)
+    p0 = torch.randn(n, device=dev).bfloat16()          # identical on all ranks
+    g_sym.copy_(g0)
+    want = g0.clone().float()
+    dist.all_reduce(want)
+    fa.allreduce_(g_sym)
+    res["allreduce_max_abs_err"] = float((g_sym.float() - want).abs().max())
+    res["allreduce_ref_scale"] = float(want.abs().max())
+
+    class F:      # minimal stand-in for optimizer._Flat
+        pass
+    for mode in ("p2p", "multicast"):
+        fa.use_multicast = "auto" if mode == "multicast" else "off"
+        f = F()
+        f.grad, f.param, f.padded = g_sym, p_sym, n
+        per = n // W
+        f.exp_avg = torch.zeros(per, device=dev)
+        f.exp_avg_sq = torch.zeros(per, device=dev)
+        g_sym.copy_(g0)
+        p_sym.copy_(p0)
+        if mode == "multicast" and not (fa._mc(fa.handle(g_sym)) and fa._mc(fa.handle(p_sym))):
+            res["multicast_available"] = False
+            continue
+        hp = dict(lr=1e-2, beta1=0.9, beta2=0.999, eps=1e-8, wd=0.01, step=1)
+        fa.allreduce_adam(f, hp, 1.0 / W)
+        torch.cuda.synchronize()
+        pr, mr, vr = p0.clone(), torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+        gsum = g0.clone()
+        dist.all_reduce(gsum)
+        ref.adamw_step_(pr, gsum, mr, vr, 1e-2, 0.9, 0.999, 1e-8, 0.01, 1, grad_scale=1.0 / W)
+        err = float((p_sym.float() - pr.float()).abs().max())
+        gathered = [torch.empty_like(p_sym) for _ in range(W)]
+        dist.all_gather(gathered, p_sym)
+        same = all(torch.equal(gathered[0], x) for x in gathered)
+        res[f"adam_{mode}_max_abs_err"] = err
+        res[f"adam_{mode}_ranks_identical"] = bool(same)
+        if mode == "multicast":
+            res["multicast_available"] = True
+
+    # ---- 2. timing at the real payload ---------------------------------------------------------------------
+    N = args.numel // (8 * W) * (8 * W)
+    G, P = fa.alloc(N, torch.bfloat16, dev), fa.alloc(N, torch.bfloat16, dev)
+    G.normal_()
+    f = F()
+    f.grad, f.param, f.padded = G, P, N
+    f.exp_avg = torch.zeros(N // W, device=dev)
+    f.exp_avg_sq = torch.zeros(N // W, device=dev)
+    hp = dict(lr=1e-5, beta1=0.9, beta2=0.999, eps=1e-8, wd=0.0, step=1)
+    for mode in ("p2p", "multicast"):
+        if mode == "multicast" and not res.get("multicast_available"):
+            continue
+        fa.use_multicast = "auto" if mode == "multicast" else "off"
+        res[f"fused_{mode}_ms"] = timed(lambda: fa.allreduce_adam(f, hp, 1.0 / W), args.iters, comm)
+    g_plain = torch.randn(N, device=dev).bfloat16()
+    p_plain = torch.zeros(N, device=dev, dtype=torch.bfloat16)
+    m_full, v_full = torch.zeros(N, device=dev), torch.zeros(N, device=dev)
+
+    def nccl_path():
+        dist.all_reduce(g_plain)
+        native.adamw_flat(p_plain, g_plain, m_full, v_full, 1e-5, 0.9, 0.999, 1e-8, 0.0, 1, 1.0 / W)
+
+    res["nccl_allreduce_plus_adam_ms"] = timed(nccl_path, args.iters, comm)
+    res["nccl_allreduce_only_ms"] = timed(lambda: dist.all_reduce(g_plain), args.iters, comm)
+    bytes_link = 2.0 * N * (W - 1) / W            # per GPU: (W-1)/W of the payload in and out
+    best = min(v for k, v in res.items() if k.startswith("fused_") and k.endswith("_ms"))
+    res["payload_gb"] = 2.0 * N / 1e9
+    res["fused_best_ms"] = best
+    res["fused_link_gbs_per_dir"] = bytes_link / (best / 1e3) / 1e9
+    res["frac_of_measured_770_gbs"] = res["fused_link_gbs_per_dir"] / 770.0
+    res["speedup_vs_nccl_plus_adam"] = res["nccl_allreduce_plus_adam_ms"] / best
+    if comm.is_main:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", f"dist_check_{W}.json"), "w") as fh:
+            json.dump(res, fh, indent=1)
+        print(json.dumps(res), flush=True)
+    ok = res["allreduce_max_abs_err"] <= 0.02 * max(res["allreduce_ref_scale"], 1.0) and res["adam_p2p_max_abs_err"] < 2e-2 \
+        and res["adam_p2p_ranks_identical"]
+    comm.barrier()
+    comm.close()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()

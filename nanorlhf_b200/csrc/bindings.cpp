@@ -329,6 +329,102 @@ torch::Tensor paged_decode(const torch::Tensor& q, const torch::Tensor& k_cache,
   return out;
 }
 
+// ---- packed-varlen flash attention ----------------------------------------------------------------------
+inline void check_thd(const torch::Tensor& t, const char* name) {
+  TORCH_CHECK(t.is_cuda() && t.scalar_type() == torch::kBFloat16 && t.dim() == 3 && t.stride(2) == 1 && t.stride(1) == t.size(2),
+              name, " must be [T, H, D] bf16 with contiguous heads");
+}
+
+std::tuple<torch::Tensor, torch::Tensor> attn_varlen_fwd(const torch::Tensor& q, const torch::Tensor& k, const torch::Tensor& v,
+                                                         const torch::Tensor& cu_seqlens, int64_t max_seqlen, double scale,
+                                                         bool causal, const c10::optional<torch::Tensor>& rel_a,
+                                                         const c10::optional<torch::Tensor>& rel_b,
+                                                         const c10::optional<torch::Tensor>& lut) {
+  check_thd(q, "q"); check_thd(k, "k"); check_thd(v, "v");
+  TORCH_CHECK(cu_seqlens.scalar_type() == torch::kInt32 && cu_seqlens.is_contiguous());
+  c10::cuda::CUDAGuard guard(q.device());
+  const int T = q.size(0), Hq = q.size(1), D = q.size(2), Hkv = k.size(1);
+  torch::Tensor out = torch::empty({T, Hq, D}, q.options());
+  torch::Tensor lse = torch::empty({Hq, T}, q.options().dtype(torch::kFloat32));
+  const void *ra = nullptr, *rb = nullptr;
+  const short* lp = nullptr;
+  int center = 0, NB = 0;
+  if (rel_a.has_value()) {
+    TORCH_CHECK(rel_b.has_value() && lut.has_value() && rel_a->is_contiguous() && rel_b->is_contiguous());
+    TORCH_CHECK(lut->scalar_type() == torch::kInt16 && lut->is_contiguous());
+    ra = rel_a->data_ptr(); rb = rel_b->data_ptr();
+    lp = reinterpret_cast<const short*>(lut->data_ptr());
+    center = (lut->numel() - 1) / 2;
+    NB = rel_a->size(2);
+    TORCH_CHECK(center >= max_seqlen - 1, "bucket LUT is too short for max_seqlen");
+    TORCH_CHECK(NB % 8 == 0);
+  }
+  check(nrl_attn_varlen_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr<float>(), q.stride(0),
+                            k.stride(0), v.stride(0), out.stride(0), cu_seqlens.data_ptr<int>(), cu_seqlens.numel() - 1, T, Hq,
+                            Hkv, D, static_cast<float>(scale), causal ? 1 : 0, ra, rb, lp, center, NB, cur_stream()),
+        "attn_varlen_fwd");
+  return {out, lse};
+}
+
+std::tuple<torch::Tensor, torch::Tensor, torch::Tensor> attn_varlen_bwd(const torch::Tensor& dout, const torch::Tensor& q,
+                                                                       const torch::Tensor& k, const torch::Tensor& v,
+                                                                       const torch::Tensor& o, const torch::Tensor& lse,
+                                                                       const torch::Tensor& cu_seqlens, int64_t max_seqlen,
+                                                                       double scale) {
+  check_thd(q, "q"); check_thd(k, "k"); check_thd(v, "v"); check_thd(o, "o"); check_thd(dout, "dout");
+  TORCH_CHECK(o.is_contiguous() && dout.is_contiguous() && dout.sizes() == o.sizes());
+  c10::cuda::CUDAGuard guard(q.device());
+  const int T = q.size(0), Hq = q.size(1), D = q.size(2), Hkv = k.size(1);
+  torch::Tensor dq = torch::empty({T, Hq, D}, q.options()), dk = torch::empty({T, Hkv, D}, q.options()),
+                dv = torch::empty({T, Hkv, D}, q.options());
+  torch::Tensor delta = torch::empty({Hq, T}, q.options().dtype(torch::kFloat32));
+  // dq/dk/dv are written with the strides of fresh contiguous tensors; q/k/v may be strided views
+  TORCH_CHECK(q.stride(0) == dq.stride(0) && k.stride(0) == dk.stride(0) && v.stride(0) == dv.stride(0),
+              "attn_varlen_bwd expects contiguous q/k/v");
+  check(nrl_attn_varlen_bwd(dout.data_ptr(), q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), lse.data_ptr<float>(),
+                            delta.data_ptr<float>(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), q.stride(0), k.stride(0),
+                            v.stride(0), o.stride(0), cu_seqlens.data_ptr<int>(), cu_seqlens.numel() - 1, T, Hq, Hkv, D,
+                            static_cast<float>(scale), cur_stream()), "attn_varlen_bwd");
+  return {dq, dk, dv};
+}
+
+// ---- K-AR: fused all-reduce + AdamW over symmetric memory ---------------------------------------------
+nrl::AdamHyper make_hyper(double lr, double beta1, double beta2, double eps, double wd, int64_t step, double grad_scale) {
+  nrl::AdamHyper h;
+  h.lr = lr; h.beta1 = beta1; h.beta2 = beta2; h.eps = eps; h.wd = wd;
+  h.step_size = static_cast<float>(lr / (1.0 - std::pow(beta1, static_cast<double>(step))));
+  h.inv_bc2 = static_cast<float>(1.0 / (1.0 - std::pow(beta2, static_cast<double>(step))));
+  h.grad_scale = grad_scale;
+  return h;
+}
+
+void allreduce_adam(const std::vector<int64_t>& grad_ptrs, const std::vector<int64_t>& param_ptrs, int64_t grad_mc,
+                    int64_t param_mc, torch::Tensor m, torch::Tensor v, int64_t lo, int64_t n, int64_t rank, double lr,
+                    double beta1, double beta2, double eps, double wd, int64_t step, double grad_scale,
+                    bool use_multicast, int64_t max_blocks) {
+  TORCH_CHECK(grad_ptrs.size() == param_ptrs.size() && !grad_ptrs.empty());
+  TORCH_CHECK(m.is_cuda() && m.is_contiguous() && v.is_contiguous() && m.numel() == n && v.numel() == n);
+  c10::cuda::CUDAGuard guard(m.device());
+  std::vector<const void*> g(grad_ptrs.size());
+  std::vector<void*> p(param_ptrs.size());
+  for (size_t i = 0; i < g.size(); ++i) {
+    g[i] = reinterpret_cast<const void*>(grad_ptrs[i]);
+    p[i] = reinterpret_cast<void*>(param_ptrs[i]);
+  }
+  check(nrl_allreduce_adam(g.data(), p.data(), reinterpret_cast<const void*>(grad_mc), reinterpret_cast<void*>(param_mc),
+                           m.data_ptr(), v.data_ptr(), lo, n, static_cast<int>(g.size()), static_cast<int>(rank),
+                           m.scalar_type() == torch::kBFloat16 ? 1 : 0, use_multicast ? 1 : 0,
+                           make_hyper(lr, beta1, beta2, eps, wd, step, grad_scale), static_cast<int>(max_blocks), cur_stream()),
+        "allreduce_adam");
+}
+
+void allreduce_sum(const std::vector<int64_t>& buf_ptrs, int64_t lo, int64_t n, int64_t rank, double scale, int64_t max_blocks) {
+  std::vector<void*> p(buf_ptrs.size());
+  for (size_t i = 0; i < p.size(); ++i) p[i] = reinterpret_cast<void*>(buf_ptrs[i]);
+  check(nrl_allreduce_sum(p.data(), lo, n, static_cast<int>(p.size()), static_cast<int>(rank), static_cast<float>(scale),
+                          static_cast<int>(max_blocks), cur_stream()), "allreduce_sum");
+}
+
 }  // namespace
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
@@ -354,5 +450,11 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("slot_mapping"), py::arg("src_index") = py::none());
   m.def("paged_decode", &paged_decode, py::arg("q"), py::arg("k_cache"), py::arg("v_cache"), py::arg("block_tables"),
         py::arg("context_lens"), py::arg("scale"), py::arg("splits") = 1, py::arg("out") = py::none());
+  m.def("attn_varlen_fwd", &attn_varlen_fwd, py::arg("q"), py::arg("k"), py::arg("v"), py::arg("cu_seqlens"), py::arg("max_seqlen"),
+        py::arg("scale"), py::arg("causal") = true, py::arg("rel_a") = py::none(), py::arg("rel_b") = py::none(),
+        py::arg("lut") = py::none());
+  m.def("attn_varlen_bwd", &attn_varlen_bwd);
+  m.def("allreduce_adam", &allreduce_adam);
+  m.def("allreduce_sum", &allreduce_sum);
   nrl::bind_runtime(m);
 }

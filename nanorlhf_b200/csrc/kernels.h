@@ -46,3 +46,22 @@ cudaError_t nrl_paged_decode(const void* q, long q_stride_s, const void* k_cache
                              float* part_ml, int S, int Hq, int Hkv, int head_dim, int page, int max_blocks, int splits,
                              float scale, cudaStream_t s);
 }
+
+extern "C" {
+cudaError_t nrl_allreduce_adam(const void* const* grad_ptrs, void* const* param_ptrs, const void* grad_mc, void* param_mc,
+                               void* m, void* v, long lo, long n, int world, int rank, int moments_bf16,
+                               int use_multicast, nrl::AdamHyper h, int max_blocks, cudaStream_t s);
+cudaError_t nrl_allreduce_sum(void* const* buf_ptrs, long lo, long n, int world, int rank, float scale, int max_blocks,
+                              cudaStream_t s);
+}
+
+extern "C" {
+cudaError_t nrl_attn_varlen_fwd(const void* q, const void* k, const void* v, void* out, float* lse, long qs, long ks,
+                                long vs, long os, const int* cu, int num_seqs, int total, int Hq, int Hkv, int D,
+                                float scale, int causal, const void* rel_a, const void* rel_b, const short* lut,
+                                int lut_center, int NB, cudaStream_t s);
+cudaError_t nrl_attn_varlen_bwd(const void* dout, const void* q, const void* k, const void* v, const void* o,
+                                const float* lse, float* delta, void* dq, void* dk, void* dv, long qs, long ks, long vs,
+                                long os, const int* cu, int num_seqs, int total, int Hq, int Hkv, int D, float scale,
+                                cudaStream_t s);
+}

@@ -114,6 +114,33 @@ class DisentangledSelfAttention(nn.Module):
         return out
 
 
+    # ---- packed / fused path (CUDA): one flash-style kernel for content + c2p + p2c ---------------------
+    def forward_packed(self, x, cu_seqlens, max_len, lut, rel_emb):
+        """x: [T_total, hidden] packed real tokens.  c2p and p2c share the index c = bucket(i-j)+span
+        (bucketing is odd in its argument), so score = (Qc.Kc + A[i,c] + B[j,c]) * scale with
+        A = Qc Kr^T and B = Kc Qr^T -- two small GEMMs feeding the fused attention kernel."""
+        from ..ops import native
+        T = x.shape[0]
+        q = self.query_proj(x).view(T, self.h, self.dh)
+        k = self.key_proj(x).view(T, self.h, self.dh)
+        v = self.value_proj(x).view(T, self.h, self.dh)
+        pos_k = self.key_proj(rel_emb).view(-1, self.h, self.dh).transpose(0, 1)          # [H, NB, dh]
+        pos_q = self.query_proj(rel_emb).view(-1, self.h, self.dh).transpose(0, 1)
+        rel_a = torch.bmm(q.transpose(0, 1), pos_k.transpose(1, 2)).contiguous()            # [H, T, NB]
+        rel_b = torch.bmm(k.transpose(0, 1), pos_q.transpose(1, 2)).contiguous()
+        scale = 1.0 / math.sqrt(self.dh * self.scale_factor)
+        native._count()
+        out, _ = native.ext().attn_varlen_fwd(q, k, v, cu_seqlens, int(max_len), scale, False, rel_a, rel_b, lut)
+        return out.reshape(T, -1)
+
+
+def build_bucket_lut(max_len: int, bucket_size: int, max_position: int, span: int, device) -> torch.Tensor:
+    """int16 table: delta in [-max_len, max_len] -> clamp(bucket(delta) + span, 0, 2*span-1)."""
+    d = torch.arange(-max_len, max_len + 1, device=device)
+    b = make_log_bucket_position(d, bucket_size, max_position) if (bucket_size > 0 and max_position > 0) else d
+    return (b + span).clamp(0, 2 * span - 1).to(torch.int16).contiguous()
+
+
 class _SelfOutput(nn.Module):
     def __init__(self, cfg):
         super().__init__()
@@ -228,8 +255,44 @@ class DebertaV3ForSequenceClassification(nn.Module):
     def forward(self, input_ids: torch.Tensor, attention_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Returns logits [B, num_labels]."""
         mask = (input_ids != self.config.pad_token_id) if attention_mask is None else attention_mask.bool()
+        if self._can_fuse(input_ids):
+            return self._forward_packed(input_ids, mask)
         h = self.deberta(input_ids, mask)
         return self.classifier(self.pooler(h)).float()
+
+    def _can_fuse(self, input_ids) -> bool:
+        if not input_ids.is_cuda or next(self.parameters()).dtype != torch.bfloat16:
+            return False
+        if os.environ.get("NANORLHF_BACKEND", "") == "torch" or os.environ.get("NANORLHF_DEBERTA", "") == "eager":
+            return False
+        cfg = self.config
+        return cfg.hidden_size // cfg.num_attention_heads == 64 and (cfg.position_buckets * 2) % 8 == 0
+
+    def _forward_packed(self, input_ids, mask):
+        """Padding-free forward: all token-wise layers run on the packed real tokens, attention in the fused
+        disentangled flash kernel (csrc/attention_varlen.cu, REL_BIAS)."""
+        cfg = self.config
+        lens = mask.sum(1)
+        cu = torch.zeros(mask.shape[0] + 1, dtype=torch.int32, device=input_ids.device)
+        cu[1:] = lens.cumsum(0)
+        max_len = input_ids.shape[1]
+        flat = mask.reshape(-1).nonzero(as_tuple=False).squeeze(1)
+        ids = input_ids.reshape(-1)[flat]
+        emb = self.deberta.embeddings
+        x = emb.LayerNorm(emb.word_embeddings(ids))
+        enc = self.deberta.encoder
+        max_rel = cfg.max_relative_positions if cfg.max_relative_positions > 0 else cfg.max_position_embeddings
+        key = (max_len, str(input_ids.device))
+        if getattr(self, "_lut_key", None) != key:
+            self._lut = build_bucket_lut(max_len, cfg.position_buckets, max_rel, cfg.position_buckets, input_ids.device)
+            self._lut_key = key
+        rel_emb = enc.LayerNorm(enc.rel_embeddings.weight)
+        for layer in enc.layer:
+            a = layer.attention.self.forward_packed(x, cu, max_len, self._lut, rel_emb)
+            a = layer.attention.output(a, x)
+            x = layer.output(layer.intermediate(a), a)
+        first = x[cu[:-1].long()]
+        return self.classifier(F.gelu(self.pooler.dense(first))).float()
 
     @classmethod
     def from_config(cls, cfg, torch_dtype=torch.bfloat16, device="cpu", seed: Optional[int] = None):

@@ -1,0 +1,80 @@
+"""Host side of K-AR: symmetric-memory allocation + the fused all-reduce/AdamW launch.
+
+``torch.distributed._symmetric_memory`` is used *only* as the allocator / handle exchanger (CUDA VMM
+allocation, fabric-handle exchange over the bootstrap process group, NVLS multicast object, signal
+pads); the data path is csrc/comm.cu -- peer / multicast loads and stores issued from inside the
+kernel.  There is no NCCL call on this path.
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, List
+
+import torch
+import torch.distributed as dist
+
+from ..ops import native
+
+
+class FusedAllReduceAdam:
+    def __init__(self, comm, use_multicast: str = "auto", max_blocks: int = 148 * 4):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.symm_mem = symm_mem
+        self.comm = comm
+        self.group = dist.group.WORLD
+        self.handles: Dict[int, object] = {}
+        self.max_blocks = max_blocks
+        self.use_multicast = os.environ.get("NANORLHF_NVLS", use_multicast)
+        self.bytes_reduced = 0
+        native.load()
+
+    def alloc(self, n: int, dtype: torch.dtype, device) -> torch.Tensor:
+        """Symmetric (peer-mapped) flat buffer.  Collective: every rank must call with the same size."""
+        t = self.symm_mem.empty(n, dtype=dtype, device=device)
+        t.zero_()
+        hdl = self.symm_mem.rendezvous(t, self.group.group_name)
+        self.handles[t.data_ptr()] = hdl
+        return t
+
+    def handle(self, t: torch.Tensor):
+        return self.handles[t.data_ptr()]
+
+    def register(self, flats: List):
+        self.flats = flats
+
+    def _mc(self, hdl) -> int:
+        if self.use_multicast in ("0", "off", "never"):
+            return 0
+        return int(getattr(hdl, "multicast_ptr", 0) or 0)
+
+    @torch.no_grad()
+    def allreduce_adam(self, f, hp: dict, scale: float):
+        """reduce-scatter(grad) + AdamW on the owned shard + all-gather(param), one kernel."""
+        gh, ph = self.handle(f.grad), self.handle(f.param)
+        world, rank = self.comm.world_size, self.comm.rank
+        per = f.padded // world
+        lo = rank * per
+        n = per if rank < world - 1 else f.padded - lo
+        mc_g, mc_p = self._mc(gh), self._mc(ph)
+        use_mc = bool(mc_g and mc_p)
+        gh.barrier(channel=0)                      # every rank's backward has finished writing its gradients
+        native._count()
+        native.ext().allreduce_adam(list(gh.buffer_ptrs), list(ph.buffer_ptrs), mc_g, mc_p, f.exp_avg, f.exp_avg_sq,
+                                    lo, n, rank, hp["lr"], hp["beta1"], hp["beta2"], hp["eps"], hp["wd"], hp["step"],
+                                    scale, use_mc, self.max_blocks)
+        ph.barrier(channel=1)                      # updated parameters are visible on every rank
+        self.bytes_reduced += f.padded * f.grad.element_size()
+
+    @torch.no_grad()
+    def allreduce_(self, t: torch.Tensor, scale: float = 1.0):
+        """In-place fused sum all-reduce of a symmetric bf16 buffer (A/B baseline for dist.all_reduce)."""
+        h = self.handle(t)
+        world, rank = self.comm.world_size, self.comm.rank
+        per = (t.numel() // world) // 8 * 8
+        lo = rank * per
+        n = per if rank < world - 1 else t.numel() - lo
+        h.barrier(channel=0)
+        native._count()
+        native.ext().allreduce_sum(list(h.buffer_ptrs), lo, n, rank, scale, self.max_blocks)
+        h.barrier(channel=1)
+        return t

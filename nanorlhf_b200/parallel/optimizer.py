@@ -103,6 +103,11 @@ class FusedAdamW(torch.optim.Optimizer):
             self._flats.append(_Flat(ps, state_dtype, grad_alloc, param_alloc))
         if self._fused is not None:
             self._fused.register([f for f in self._flats if f is not None])
+        if self.world > 1:
+            # replicas must start identical (DDP broadcasts rank 0's parameters at construction);
+            # one flat broadcast per group over the bootstrap process group
+            for f in self.flats:
+                comm.broadcast_(f.param, 0)
 
     # ---- bookkeeping -----------------------------------------------------------------------
     @property

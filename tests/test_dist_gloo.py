@@ -1,0 +1,48 @@
+"""Host-side data-parallel logic under gloo, world_size 2, on the CPU box ("multi-node without a cluster")."""
+import os
+import tempfile
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+
+def _worker(rank, world, port, tmp, algo):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    torch.set_num_threads(2)
+    from dataclasses import dataclass
+    from nanorlhf_b200.config import RLConfig
+    from nanorlhf_b200.models.lora import LoraConfig, get_peft_model
+    from nanorlhf_b200.models.qwen2 import Qwen2Config, Qwen2ForCausalLM
+    from nanorlhf_b200.parallel.comm import Comm
+    from nanorlhf_b200.reward.api import LengthReward
+    from nanorlhf_b200.trainer import GRPOTrainer, SparseGRPOTrainer
+    from nanorlhf_b200.utils.data import synthetic_hh_dataset
+    from nanorlhf_b200.utils.tokenizer import ByteTokenizer
+    comm = Comm.from_env(torch.device("cpu"))
+    tok = ByteTokenizer()
+    cfg = Qwen2Config.tiny(vocab_size=tok.vocab_size)
+    policy = get_peft_model(Qwen2ForCausalLM.from_config(cfg, torch.float32, seed=1), LoraConfig(r=4, lora_alpha=8, modules_to_save=None))
+    ref = Qwen2ForCausalLM.from_config(cfg, torch.float32, seed=1)
+    a = RLConfig(output_dir=tmp, response_length=8, per_device_train_batch_size=2, gradient_accumulation_steps=1,
+                 num_mini_batches=2, total_episodes=16, learning_rate=1e-3, sampler="torch", report_to="none")
+    a.grpo_sample_N = 4
+    a.quiet = True
+    cls = SparseGRPOTrainer if algo == "sparse" else GRPOTrainer
+    # rank-dependent reward => rank-dependent number of surviving rows in sparse GRPO (deadlock regression)
+    reward = LengthReward(4 + 3 * rank)
+    t = cls(a, tok, policy, ref, synthetic_hh_dataset(tok, 32, max_prompt_tokens=20), reward_func=reward, comm=comm)
+    t.train()
+    flat = torch.cat([p.detach().reshape(-1) for p in t.policy.parameters() if p.requires_grad])
+    both = comm.all_gather_cat(flat[None])
+    assert torch.equal(both[0], both[1]), "ranks diverged: gradients were not averaged identically"
+    assert t.state.global_step == 2 and t.state.episode == 16
+    comm.close()
+
+
+@pytest.mark.parametrize("algo", ["grpo", "sparse"])
+def test_two_rank_training_keeps_replicas_identical(algo):
+    port = 29600 + (os.getpid() % 200) + (0 if algo == "grpo" else 1)
+    with tempfile.TemporaryDirectory() as tmp:
+        mp.spawn(_worker, args=(2, port, tmp, algo), nprocs=2, join=True)

@@ -226,3 +226,49 @@ def test_paged_decode(Hq, Hkv, splits):
     n.kv_cache_write(k, v, kc, vc, slots)
     blk, off = (slots // bs).long(), (slots % bs).long()
     assert torch.equal(kc[blk, :, off], k) and torch.equal(vc[blk, :, off], v)
+
+
+@pytest.mark.parametrize("Hq,Hkv,D", [(12, 2, 128), (4, 4, 64)])
+def test_attention_varlen_fwd_bwd(Hq, Hkv, D):
+    n = _native()
+    torch.manual_seed(0)
+    lens = [1, 17, 64, 65, 200, 333]
+    cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32, device="cuda")
+    T = sum(lens)
+    q = torch.randn(T, Hq, D, device="cuda").bfloat16().requires_grad_(True)
+    k = torch.randn(T, Hkv, D, device="cuda").bfloat16().requires_grad_(True)
+    v = torch.randn(T, Hkv, D, device="cuda").bfloat16().requires_grad_(True)
+    from nanorlhf_b200.ops.attention import _NativeAttn
+    o = _NativeAttn.apply(q, k, v, cu, max(lens), 1.0 / math.sqrt(D))
+    g = torch.randn_like(o)
+    o.backward(g)
+    qr, kr, vr = (t.detach().float().requires_grad_(True) for t in (q, k, v))
+    orf = ref.attention_varlen(qr, kr, vr, cu.cpu(), causal=True)
+    orf.backward(g.float())
+    assert _rel(o, orf) < 2e-2
+    assert _rel(q.grad, qr.grad) < 3e-2 and _rel(k.grad, kr.grad) < 3e-2 and _rel(v.grad, vr.grad) < 3e-2
+
+
+def test_deberta_fused_attention_matches_eager():
+    import os
+    from nanorlhf_b200.models.deberta_v3 import DebertaV3Config, DebertaV3ForSequenceClassification
+    cfg = DebertaV3Config(vocab_size=1000, hidden_size=256, num_hidden_layers=3, num_attention_heads=4, intermediate_size=512,
+                          position_buckets=256, max_position_embeddings=512, pooler_hidden_size=256)
+    m = DebertaV3ForSequenceClassification.from_config(cfg, torch.bfloat16, "cuda", seed=0)
+    with torch.no_grad():
+        for p in m.parameters():
+            p.mul_(3.0)            # make attention non-trivial
+    ids = torch.randint(3, 1000, (5, 700), device="cuda")
+    ids[0, 650:] = 0
+    ids[2, 33:] = 0
+    ids[4, 1:] = 0
+    fused = m(ids)
+    os.environ["NANORLHF_DEBERTA"] = "eager"
+    try:
+        eager = m(ids)
+        ref32 = m.float()(ids)
+    finally:
+        os.environ.pop("NANORLHF_DEBERTA")
+    # the fused bf16 path must be as close to the fp32 model as the eager bf16 path is
+    err_f, err_e = (fused - ref32).abs().max().item(), (eager - ref32).abs().max().item()
+    assert err_f < max(3 * err_e, 3e-2), (err_f, err_e)
