@@ -187,7 +187,8 @@ __global__ void __launch_bounds__(128) flash_fwd_kernel(AttnParams p) {
         const int row = (e < 2) ? row_a : row_b;
         float x = s[nt][e];
         if (REL_BIAS) {
-          const int c = p.bucket_lut[row - key + p.lut_center];
+          // rows/keys of the padded tail of the last block fall outside the table: clamp (their scores are masked)
+          const int c = p.bucket_lut[min(max(row - key, -p.lut_center), p.lut_center) + p.lut_center];
           const __nv_bfloat16* ar = reinterpret_cast<const __nv_bfloat16*>(sA) + static_cast<long>(row - q0) * p.NB;
           const __nv_bfloat16* br = reinterpret_cast<const __nv_bfloat16*>(sB + static_cast<long>(buf) * BN * p.NB * 2) +
                                     static_cast<long>(key - key0) * p.NB;

@@ -135,6 +135,28 @@ torch::Tensor lmhead_dlogits(const torch::Tensor& hidden, const torch::Tensor& w
   return dz;
 }
 
+// K-BC: out[N_out, K_in] = W + scale * lora_B[N_out, r] @ lora_A[r, K_in], on the tcgen05 GEMM (contraction = r)
+void lora_merge(const torch::Tensor& w, const torch::Tensor& lora_a, const torch::Tensor& lora_b, double scale, torch::Tensor out) {
+  check_bf16_2d(w, "w");
+  check_bf16_2d(lora_b, "lora_B");
+  check_bf16_2d(out, "out");
+  TORCH_CHECK(lora_a.is_cuda() && lora_a.scalar_type() == torch::kBFloat16 && lora_a.dim() == 2);
+  const int64_t N_out = w.size(0), K_in = w.size(1), r = lora_a.size(0);
+  TORCH_CHECK(lora_b.size(0) == N_out && lora_b.size(1) == r && lora_a.size(1) == K_in && out.sizes() == w.sizes());
+  TORCH_CHECK(r % 8 == 0 && K_in % 8 == 0);
+  c10::cuda::CUDAGuard guard(w.device());
+  torch::Tensor a_t = lora_a.t().contiguous();                      // [K_in, r]: the B operand, contraction-major
+  const int bn = 256;
+  CUtensorMap tmA = nrl::make_tma_2d(lora_b.data_ptr(), N_out, r, lora_b.stride(0) * 2, 128, 64, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2);
+  CUtensorMap tmB = nrl::make_tma_2d(a_t.data_ptr(), K_in, r, a_t.stride(0) * 2, bn, 64, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2);
+  CUtensorMap tmD = nrl::make_tma_2d(out.data_ptr(), N_out, K_in, out.stride(0) * 2, 128, 64, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2);
+  nrl::GemmParams p{};
+  p.M = N_out; p.N = K_in; p.K = r; p.n_splits = 1; p.scale = static_cast<float>(scale);
+  p.addend = reinterpret_cast<const __nv_bfloat16*>(w.data_ptr());
+  p.addend_stride = w.stride(0);
+  check(nrl_gemm_bf16_tn(&tmA, &tmB, &tmD, &p, bn, nrl::EPI_MERGE, num_sms(), cur_stream()), "lora_merge");
+}
+
 // ---- elementwise --------------------------------------------------------------------------------
 std::tuple<torch::Tensor, torch::Tensor, torch::Tensor> rmsnorm(const torch::Tensor& x, const torch::Tensor& w, double eps,
                                                                 const c10::optional<torch::Tensor>& residual,
@@ -434,6 +456,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("lmhead_logprob_fwd", &lmhead_logprob_fwd, py::arg("hidden"), py::arg("weight"), py::arg("targets"),
         py::arg("inv_temperature"), py::arg("n_splits") = 0);
   m.def("lmhead_dlogits", &lmhead_dlogits);
+  m.def("lora_merge", &lora_merge);
   m.def("rmsnorm", &rmsnorm, py::arg("x"), py::arg("w"), py::arg("eps"), py::arg("residual") = py::none(),
         py::arg("want_rstd") = false);
   m.def("rmsnorm_bwd", &rmsnorm_bwd);

@@ -275,7 +275,18 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 float x0 = __uint_as_float(v[h][j]);
                 float x1 = __uint_as_float(v[h][j + 1]);
                 const int col = col0 + h * 32 + j;
-                if (EPI == EPI_STORE) {
+                if (EPI == EPI_MERGE) {
+                  // K-BC: merged weight = W + (alpha/r) * (B A); W streamed straight from HBM in the epilogue
+                  x0 *= p.scale;
+                  x1 *= p.scale;
+                  if (row_ok && col + 1 < p.N) {
+                    float2 w2 = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(p.addend + static_cast<long>(row) * p.addend_stride + col));
+                    x0 += w2.x;
+                    x1 += w2.y;
+                  } else if (row_ok && col < p.N) {
+                    x0 += __bfloat162float(p.addend[static_cast<long>(row) * p.addend_stride + col]);
+                  }
+                } else if (EPI == EPI_STORE) {
                   if (p.bias != nullptr) {
                     if (col < p.N) x0 += __bfloat162float(p.bias[col]);
                     if (col + 1 < p.N) x1 += __bfloat162float(p.bias[col + 1]);
@@ -380,7 +391,9 @@ extern "C" cudaError_t nrl_gemm_bf16_tn(const CUtensorMap* tmA, const CUtensorMa
     if (epi == EPI_STORE) return launch_impl<256, EPI_STORE>(*tmA, *tmB, *tmD, *p, num_sms, stream);
     if (epi == EPI_LOGPROB) return launch_impl<256, EPI_LOGPROB>(*tmA, *tmB, *tmD, *p, num_sms, stream);
     if (epi == EPI_DLOGITS) return launch_impl<256, EPI_DLOGITS>(*tmA, *tmB, *tmD, *p, num_sms, stream);
+    if (epi == EPI_MERGE) return launch_impl<256, EPI_MERGE>(*tmA, *tmB, *tmD, *p, num_sms, stream);
   } else if (block_n == 128) {
+    if (epi == EPI_MERGE) return launch_impl<128, EPI_MERGE>(*tmA, *tmB, *tmD, *p, num_sms, stream);
     if (epi == EPI_STORE) return launch_impl<128, EPI_STORE>(*tmA, *tmB, *tmD, *p, num_sms, stream);
     if (epi == EPI_LOGPROB) return launch_impl<128, EPI_LOGPROB>(*tmA, *tmB, *tmD, *p, num_sms, stream);
     if (epi == EPI_DLOGITS) return launch_impl<128, EPI_DLOGITS>(*tmA, *tmB, *tmD, *p, num_sms, stream);

@@ -10,6 +10,7 @@ enum GemmEpilogue : int {
   EPI_STORE = 0,     // D = A B^T (+ bias)                      -> bf16 [M,N]
   EPI_LOGPROB = 1,   // fused lm-head log-prob partials          -> float4 [n_splits, M]
   EPI_DLOGITS = 2,   // dZ = (onehot - softmax) * g / T          -> bf16 [M,N]
+  EPI_MERGE = 3,     // D = addend + scale * (A B^T)  (K-BC LoRA merge: W + (alpha/r) B A) -> bf16 [M,N]
 };
 
 struct GemmParams {
@@ -21,6 +22,8 @@ struct GemmParams {
   const float* lse;             // EPI_DLOGITS: [M]
   const float* grad_logp;       // EPI_DLOGITS: [M]
   float* partials;              // EPI_LOGPROB: [n_splits, M, 4]
+  const __nv_bfloat16* addend;  // EPI_MERGE: [M, N] row-major, row stride addend_stride elements
+  long addend_stride;
 };
 
 }  // namespace nrl

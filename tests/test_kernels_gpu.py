@@ -272,3 +272,20 @@ def test_deberta_fused_attention_matches_eager():
     # the fused bf16 path must be as close to the fp32 model as the eager bf16 path is
     err_f, err_e = (fused - ref32).abs().max().item(), (eager - ref32).abs().max().item()
     assert err_f < max(3 * err_e, 3e-2), (err_f, err_e)
+
+
+def test_lora_merge_kernel():
+    n = _native()
+    torch.manual_seed(0)
+    for (N, K, r) in ((1536, 1536, 64), (17920 // 2, 1536, 64), (1536, 8960, 64), (256, 1536, 64)):
+        w = torch.randn(N, K, device="cuda").bfloat16()
+        a = (torch.randn(r, K, device="cuda") * 0.1).bfloat16()
+        b = (torch.randn(N, r, device="cuda") * 0.1).bfloat16()
+        out = torch.empty_like(w)
+        n.ext().lora_merge(w, a, b, 0.25, out)
+        want = w.float() + 0.25 * (b.float() @ a.float())
+        assert _rel(out, want) < 5e-3
+        # writing into a row-slice of a larger (fused qkv-style) arena
+        arena = torch.zeros(N + 64, K, device="cuda", dtype=torch.bfloat16)
+        n.ext().lora_merge(w, a, b, 0.25, arena[32:32 + N])
+        assert torch.equal(arena[32:32 + N], out) and arena[:32].abs().sum() == 0 and arena[32 + N:].abs().sum() == 0
