@@ -90,6 +90,14 @@ NRL_DEVICE void load_tile_async(uint8_t* smem_tile, const __nv_bfloat16* base, l
   }
 }
 
+constexpr int kRelBW = 112;   // staged window of the key-side bias table: >= 64 + 32 - 1 + 7, multiple of 8
+
+// first (8-aligned) table column needed by the score tile (rows q0..q0+63, keys k0..k0+BN-1)
+NRL_DEVICE int rel_window_lo(const AttnParams& p, int q0, int k0, int BN) {
+  const int dmin = q0 - (k0 + BN - 1);
+  return p.bucket_lut[min(max(dmin, -p.lut_center), p.lut_center) + p.lut_center] & ~7;
+}
+
 // =================================================================================================
 // forward
 // =================================================================================================
@@ -101,7 +109,7 @@ __global__ void __launch_bounds__(128) flash_fwd_kernel(AttnParams p) {
   uint8_t* sK = sQ + BM * D * 2;                   // [2][BN][D]
   uint8_t* sV = sK + 2 * BN * D * 2;               // [2][BN][D]
   uint8_t* sA = sV + 2 * BN * D * 2;               // REL_BIAS: [64][NB] bf16
-  uint8_t* sB = sA + (REL_BIAS ? BM * p.NB * 2 : 0);   // REL_BIAS: [2][BN][NB] bf16
+  uint8_t* sB = sA + (REL_BIAS ? BM * p.NB * 2 : 0);   // REL_BIAS: [2][BN][kRelBW] bf16 (column window, see below)
 
   int seq, m_blk, seq_start, seq_len;
   if (!locate_block<BM>(p.cu_seqlens, p.num_seqs, blockIdx.x, seq, m_blk, seq_start, seq_len)) return;
@@ -128,14 +136,17 @@ __global__ void __launch_bounds__(128) flash_fwd_kernel(AttnParams p) {
     load_tile_async<D, BN, 128>(sK + buf * BN * D * 2, kbase, p.k_stride_t, kvh, nb * BN, seq_len);
     load_tile_async<D, BN, 128>(sV + buf * BN * D * 2, vbase, p.v_stride_t, kvh, nb * BN, seq_len);
     if (REL_BIAS) {
-      const int CH = p.NB / 8;
+      // The bucket index c(i-j) is monotone in (i-j) with slope <= 1, so a (64 x BN) score tile touches at
+      // most 64+BN-1 consecutive table columns: stage only that window of B (not all NB columns).
+      const int CH = kRelBW / 8;
+      const int c_lo = rel_window_lo(p, q0, nb * BN, BN);
       const __nv_bfloat16* bbase = p.rel_b + (static_cast<long>(head) * p.total_tokens + seq_start) * p.NB;
-      uint8_t* dst = sB + static_cast<long>(buf) * BN * p.NB * 2;
+      uint8_t* dst = sB + static_cast<long>(buf) * BN * kRelBW * 2;
       for (int i = threadIdx.x; i < BN * CH; i += 128) {
         const int r = i / CH, c = i % CH;
-        const bool ok = (nb * BN + r) < seq_len;
-        cp_async_16_zfill(dst + (static_cast<long>(r) * p.NB + c * 8) * 2,
-                          bbase + static_cast<long>(ok ? nb * BN + r : nb * BN) * p.NB + c * 8, ok);
+        const bool ok = ((nb * BN + r) < seq_len) && (c_lo + c * 8 < p.NB);
+        cp_async_16_zfill(dst + (static_cast<long>(r) * kRelBW + c * 8) * 2,
+                          bbase + static_cast<long>(ok ? nb * BN + r : nb * BN) * p.NB + (ok ? c_lo + c * 8 : 0), ok);
       }
     }
   };
@@ -179,6 +190,7 @@ __global__ void __launch_bounds__(128) flash_fwd_kernel(AttnParams p) {
     }
     // ---- scale, bias, mask ----
     const int key0 = nb * BN;
+    const int c_lo_cur = REL_BIAS ? rel_window_lo(p, q0, key0, BN) : 0;
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
@@ -190,9 +202,9 @@ __global__ void __launch_bounds__(128) flash_fwd_kernel(AttnParams p) {
           // rows/keys of the padded tail of the last block fall outside the table: clamp (their scores are masked)
           const int c = p.bucket_lut[min(max(row - key, -p.lut_center), p.lut_center) + p.lut_center];
           const __nv_bfloat16* ar = reinterpret_cast<const __nv_bfloat16*>(sA) + static_cast<long>(row - q0) * p.NB;
-          const __nv_bfloat16* br = reinterpret_cast<const __nv_bfloat16*>(sB + static_cast<long>(buf) * BN * p.NB * 2) +
-                                    static_cast<long>(key - key0) * p.NB;
-          x += __bfloat162float(ar[c]) + __bfloat162float(br[c]);
+          const __nv_bfloat16* br = reinterpret_cast<const __nv_bfloat16*>(sB + static_cast<long>(buf) * BN * kRelBW * 2) +
+                                    static_cast<long>(key - key0) * kRelBW;
+          x += __bfloat162float(ar[c]) + __bfloat162float(br[min(max(c - c_lo_cur, 0), kRelBW - 1)]);
         }
         x *= p.scale_log2;
         const bool dead = (key >= seq_len) || (CAUSAL && key > row);
@@ -599,7 +611,7 @@ extern "C" cudaError_t nrl_attn_varlen_fwd(const void* q, const void* k, const v
   if (rel_a != nullptr) {
     if (D != 64 || causal) return cudaErrorInvalidValue;
     constexpr int BN = 32;
-    const int smem = 64 * 64 * 2 + 4 * BN * 64 * 2 + 64 * NB * 2 + 2 * BN * NB * 2;
+    const int smem = 64 * 64 * 2 + 4 * BN * 64 * 2 + 64 * NB * 2 + 2 * BN * kRelBW * 2;
     auto kern = flash_fwd_kernel<64, false, true, BN>;
     if ((e = set_smem(kern, smem)) != cudaSuccess) return e;
     kern<<<grid, 128, smem, s>>>(p);

@@ -205,17 +205,41 @@ torch::Tensor rope(const torch::Tensor& x, const torch::Tensor& cos_t, const tor
 torch::Tensor swiglu(const torch::Tensor& gu) {
   TORCH_CHECK(gu.is_cuda() && gu.scalar_type() == torch::kBFloat16 && gu.is_contiguous() && gu.dim() == 2 && gu.size(1) % 16 == 0);
   c10::cuda::CUDAGuard guard(gu.device());
-  torch::Tensor out = torch::empty({gu.size(0), gu.size(1) / 2}, gu.options());
-  check(nrl_swiglu(gu.data_ptr(), out.data_ptr(), gu.size(0), gu.size(1) / 2, cur_stream()), "swiglu");
+  const int64_t F = gu.size(1) / 2;
+  torch::Tensor out = torch::empty({gu.size(0), F}, gu.options());
+  auto base = reinterpret_cast<const __nv_bfloat16*>(gu.data_ptr());
+  check(nrl_swiglu(base, base + F, 2 * F, out.data_ptr(), gu.size(0), F, cur_stream()), "swiglu");
   return out;
 }
 
 torch::Tensor swiglu_bwd(const torch::Tensor& gu, const torch::Tensor& gout) {
   TORCH_CHECK(gu.is_contiguous() && gout.is_contiguous() && gout.scalar_type() == torch::kBFloat16);
   c10::cuda::CUDAGuard guard(gu.device());
+  const int64_t F = gu.size(1) / 2;
   torch::Tensor dgu = torch::empty_like(gu);
-  check(nrl_swiglu_bwd(gu.data_ptr(), gout.data_ptr(), dgu.data_ptr(), gu.size(0), gu.size(1) / 2, cur_stream()), "swiglu_bwd");
+  auto base = reinterpret_cast<const __nv_bfloat16*>(gu.data_ptr());
+  auto dbase = reinterpret_cast<__nv_bfloat16*>(dgu.data_ptr());
+  check(nrl_swiglu_bwd(base, base + F, 2 * F, gout.data_ptr(), dbase, dbase + F, 2 * F, gu.size(0), F, cur_stream()), "swiglu_bwd");
   return dgu;
+}
+
+// separate gate / up tensors (no concatenation copy)
+torch::Tensor swiglu_pair(const torch::Tensor& gate, const torch::Tensor& up) {
+  TORCH_CHECK(gate.is_cuda() && gate.scalar_type() == torch::kBFloat16 && gate.is_contiguous() && up.is_contiguous() &&
+              gate.dim() == 2 && gate.sizes() == up.sizes() && gate.size(1) % 8 == 0);
+  c10::cuda::CUDAGuard guard(gate.device());
+  torch::Tensor out = torch::empty_like(gate);
+  check(nrl_swiglu(gate.data_ptr(), up.data_ptr(), gate.size(1), out.data_ptr(), gate.size(0), gate.size(1), cur_stream()), "swiglu_pair");
+  return out;
+}
+
+std::tuple<torch::Tensor, torch::Tensor> swiglu_pair_bwd(const torch::Tensor& gate, const torch::Tensor& up, const torch::Tensor& gout) {
+  TORCH_CHECK(gate.is_contiguous() && up.is_contiguous() && gout.is_contiguous());
+  c10::cuda::CUDAGuard guard(gate.device());
+  torch::Tensor dg = torch::empty_like(gate), du = torch::empty_like(up);
+  check(nrl_swiglu_bwd(gate.data_ptr(), up.data_ptr(), gate.size(1), gout.data_ptr(), dg.data_ptr(), du.data_ptr(), gate.size(1),
+                       gate.size(0), gate.size(1), cur_stream()), "swiglu_pair_bwd");
+  return {dg, du};
 }
 
 // ---- RL kernels -----------------------------------------------------------------------------------
@@ -463,6 +487,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("rope", &rope, py::arg("x"), py::arg("cos"), py::arg("sin"), py::arg("sin_sign") = 1.0, py::arg("inplace") = false);
   m.def("swiglu", &swiglu);
   m.def("swiglu_bwd", &swiglu_bwd);
+  m.def("swiglu_pair", &swiglu_pair);
+  m.def("swiglu_pair_bwd", &swiglu_pair_bwd);
   m.def("gae_scan", &gae_scan, py::arg("rewards"), py::arg("values") = py::none(), py::arg("gamma") = 1.0, py::arg("lam") = 1.0);
   m.def("policy_loss", &policy_loss);
   m.def("value_loss", &value_loss);

@@ -171,15 +171,16 @@ __global__ void rope_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* 
 
 // ---- SwiGLU -----------------------------------------------------------------------------------
 // gate_up: [T, 2F] = [gate | up]; out[T, F] = silu(gate) * up
-__global__ void swiglu_kernel(const __nv_bfloat16* __restrict__ gu, __nv_bfloat16* __restrict__ out, long T, int F) {
+__global__ void swiglu_kernel(const __nv_bfloat16* __restrict__ gate, const __nv_bfloat16* __restrict__ up, long in_stride,
+                              __nv_bfloat16* __restrict__ out, long T, int F) {
   const int vecs = F / 8;
   const long total = T * vecs;
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long>(gridDim.x) * blockDim.x) {
     long t = i / vecs;
     int v = i % vecs;
-    uint4 g = *reinterpret_cast<const uint4*>(gu + t * 2 * F + v * 8);
-    uint4 u = *reinterpret_cast<const uint4*>(gu + t * 2 * F + F + v * 8);
+    uint4 g = *reinterpret_cast<const uint4*>(gate + t * in_stride + v * 8);
+    uint4 u = *reinterpret_cast<const uint4*>(up + t * in_stride + v * 8);
     uint32_t gw[4] = {g.x, g.y, g.z, g.w}, uw[4] = {u.x, u.y, u.z, u.w}, o[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -193,16 +194,17 @@ __global__ void swiglu_kernel(const __nv_bfloat16* __restrict__ gu, __nv_bfloat1
 }
 
 // d gate = g * up * (sig + gate*sig*(1-sig)) ; d up = g * silu(gate)
-__global__ void swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ gu, const __nv_bfloat16* __restrict__ gout,
-                                  __nv_bfloat16* __restrict__ dgu, long T, int F) {
+__global__ void swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ gate, const __nv_bfloat16* __restrict__ up, long in_stride,
+                                  const __nv_bfloat16* __restrict__ gout, __nv_bfloat16* __restrict__ dgate,
+                                  __nv_bfloat16* __restrict__ dup, long out_stride, long T, int F) {
   const int vecs = F / 8;
   const long total = T * vecs;
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long>(gridDim.x) * blockDim.x) {
     long t = i / vecs;
     int v = i % vecs;
-    uint4 g = *reinterpret_cast<const uint4*>(gu + t * 2 * F + v * 8);
-    uint4 u = *reinterpret_cast<const uint4*>(gu + t * 2 * F + F + v * 8);
+    uint4 g = *reinterpret_cast<const uint4*>(gate + t * in_stride + v * 8);
+    uint4 u = *reinterpret_cast<const uint4*>(up + t * in_stride + v * 8);
     uint4 go = *reinterpret_cast<const uint4*>(gout + t * F + v * 8);
     uint32_t gw[4] = {g.x, g.y, g.z, g.w}, uw[4] = {u.x, u.y, u.z, u.w}, ow[4] = {go.x, go.y, go.z, go.w};
     uint32_t dg[4], du[4];
@@ -213,8 +215,8 @@ __global__ void swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ gu, const __
       dg[j] = pack_bf16x2(o.x * b.x * (s0 + a.x * s0 * (1.f - s0)), o.y * b.y * (s1 + a.y * s1 * (1.f - s1)));
       du[j] = pack_bf16x2(o.x * a.x * s0, o.y * a.y * s1);
     }
-    *reinterpret_cast<uint4*>(dgu + t * 2 * F + v * 8) = make_uint4(dg[0], dg[1], dg[2], dg[3]);
-    *reinterpret_cast<uint4*>(dgu + t * 2 * F + F + v * 8) = make_uint4(du[0], du[1], du[2], du[3]);
+    *reinterpret_cast<uint4*>(dgate + t * out_stride + v * 8) = make_uint4(dg[0], dg[1], dg[2], dg[3]);
+    *reinterpret_cast<uint4*>(dup + t * out_stride + v * 8) = make_uint4(du[0], du[1], du[2], du[3]);
   }
 }
 
@@ -265,19 +267,23 @@ extern "C" cudaError_t nrl_rope(const void* x, void* y, const float* cos_t, cons
   return cudaGetLastError();
 }
 
-extern "C" cudaError_t nrl_swiglu(const void* gu, void* out, long T, int F, cudaStream_t s) {
-  if (F % 8 != 0) return cudaErrorInvalidValue;
+extern "C" cudaError_t nrl_swiglu(const void* gate, const void* up, long in_stride, void* out, long T, int F,
+                                  cudaStream_t s) {
+  if (F % 8 != 0 || in_stride % 8 != 0) return cudaErrorInvalidValue;
   if (T == 0) return cudaSuccess;
-  swiglu_kernel<<<grid_for(T * (F / 8), 256), 256, 0, s>>>(static_cast<const __nv_bfloat16*>(gu),
+  swiglu_kernel<<<grid_for(T * (F / 8), 256), 256, 0, s>>>(static_cast<const __nv_bfloat16*>(gate),
+                                                          static_cast<const __nv_bfloat16*>(up), in_stride,
                                                           static_cast<__nv_bfloat16*>(out), T, F);
   return cudaGetLastError();
 }
 
-extern "C" cudaError_t nrl_swiglu_bwd(const void* gu, const void* gout, void* dgu, long T, int F, cudaStream_t s) {
-  if (F % 8 != 0) return cudaErrorInvalidValue;
+extern "C" cudaError_t nrl_swiglu_bwd(const void* gate, const void* up, long in_stride, const void* gout, void* dgate,
+                                      void* dup, long out_stride, long T, int F, cudaStream_t s) {
+  if (F % 8 != 0 || in_stride % 8 != 0 || out_stride % 8 != 0) return cudaErrorInvalidValue;
   if (T == 0) return cudaSuccess;
-  swiglu_bwd_kernel<<<grid_for(T * (F / 8), 256), 256, 0, s>>>(static_cast<const __nv_bfloat16*>(gu),
-                                                              static_cast<const __nv_bfloat16*>(gout),
-                                                              static_cast<__nv_bfloat16*>(dgu), T, F);
+  swiglu_bwd_kernel<<<grid_for(T * (F / 8), 256), 256, 0, s>>>(
+      static_cast<const __nv_bfloat16*>(gate), static_cast<const __nv_bfloat16*>(up), in_stride,
+      static_cast<const __nv_bfloat16*>(gout), static_cast<__nv_bfloat16*>(dgate), static_cast<__nv_bfloat16*>(dup),
+      out_stride, T, F);
   return cudaGetLastError();
 }

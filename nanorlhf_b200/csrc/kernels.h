@@ -19,8 +19,9 @@ cudaError_t nrl_rmsnorm_bwd(const void* x, const void* w, const void* gy, const 
                             cudaStream_t s);
 cudaError_t nrl_rope(const void* x, void* y, const float* cos_t, const float* sin_t, int T, int H, int D,
                      long x_stride_t, long y_stride_t, float sin_sign, cudaStream_t s);
-cudaError_t nrl_swiglu(const void* gu, void* out, long T, int F, cudaStream_t s);
-cudaError_t nrl_swiglu_bwd(const void* gu, const void* gout, void* dgu, long T, int F, cudaStream_t s);
+cudaError_t nrl_swiglu(const void* gate, const void* up, long in_stride, void* out, long T, int F, cudaStream_t s);
+cudaError_t nrl_swiglu_bwd(const void* gate, const void* up, long in_stride, const void* gout, void* dgate, void* dup,
+                           long out_stride, long T, int F, cudaStream_t s);
 
 cudaError_t nrl_gae_scan(const float* rewards, const float* values, float* adv, float* returns, int B, int T,
                          float gamma, float lam, cudaStream_t s);

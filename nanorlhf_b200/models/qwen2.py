@@ -134,8 +134,7 @@ class Qwen2MLP(nn.Module):
         self.down_proj = nn.Linear(cfg.intermediate_size, cfg.hidden_size, bias=False)
 
     def forward(self, x):
-        gu = torch.cat([self.gate_proj(x), self.up_proj(x)], dim=-1)
-        return self.down_proj(ops.swiglu(gu))
+        return self.down_proj(ops.swiglu_pair(self.gate_proj(x), self.up_proj(x)))
 
 
 class Qwen2DecoderLayer(nn.Module):

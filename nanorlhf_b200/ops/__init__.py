@@ -73,6 +73,13 @@ def swiglu(gate_up):
     return ref.swiglu(gate_up)
 
 
+def swiglu_pair(gate, up):
+    """silu(gate) * up without concatenating the two projections."""
+    if use_native(gate):
+        return _nat().swiglu_pair(gate, up)
+    return (torch.nn.functional.silu(gate.float()) * up.float()).to(gate.dtype)
+
+
 def attention_varlen(q, k, v, cu_seqlens, max_seqlen=None, causal=True, scale=None):
     if use_native(q):
         return _nat().attention_varlen(q, k, v, cu_seqlens, max_seqlen, causal, scale)

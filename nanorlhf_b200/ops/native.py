@@ -162,6 +162,29 @@ def swiglu(gate_up):
     return _SwigluFn.apply(gate_up)
 
 
+class _SwigluPairFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, gate, up):
+        g2 = gate.reshape(-1, gate.shape[-1]).contiguous()
+        u2 = up.reshape(-1, up.shape[-1]).contiguous()
+        ctx.save_for_backward(g2, u2)
+        _count()
+        return ext().swiglu_pair(g2, u2).view(gate.shape)
+
+    @staticmethod
+    def backward(ctx, go):
+        g2, u2 = ctx.saved_tensors
+        _count()
+        dg, du = ext().swiglu_pair_bwd(g2, u2, go.reshape(-1, go.shape[-1]).contiguous())
+        return dg.view(go.shape), du.view(go.shape)
+
+
+def swiglu_pair(gate, up):
+    if gate.dtype != torch.bfloat16:
+        return (F.silu(gate.float()) * up.float()).to(gate.dtype)
+    return _SwigluPairFn.apply(gate, up)
+
+
 # --------------------------------------------------------------------------------------------
 # attention
 # --------------------------------------------------------------------------------------------
