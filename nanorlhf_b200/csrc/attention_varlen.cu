@@ -190,25 +190,49 @@ __global__ void __launch_bounds__(128) flash_fwd_kernel(AttnParams p) {
     }
     // ---- scale, bias, mask ----
     const int key0 = nb * BN;
-    const int c_lo_cur = REL_BIAS ? rel_window_lo(p, q0, key0, BN) : 0;
+    if (REL_BIAS) {
+      const int c_lo_cur = rel_window_lo(p, q0, key0, BN);
+      const short* lut = p.bucket_lut + p.lut_center;
+      const int dmin = max(q0 - (key0 + BN - 1), -p.lut_center), dmax = min(q0 + BM - 1 - key0, p.lut_center);
+      const int c_min = lut[dmin], c_max = lut[dmax];
+      const __nv_bfloat16* aw = reinterpret_cast<const __nv_bfloat16*>(sA);
+      const __nv_bfloat16* bw = reinterpret_cast<const __nv_bfloat16*>(sB + static_cast<long>(buf) * BN * kRelBW * 2);
+      const __nv_bfloat16* ar_a = aw + static_cast<long>(row_a - q0) * p.NB;
+      const __nv_bfloat16* ar_b = aw + static_cast<long>(row_b - q0) * p.NB;
+      if (c_min == c_max) {
+        // far-from-diagonal tile: one bucket for every (i, j) -> bias = A[i, c0] + B[j, c0] (rank-1, no lookups)
+        const float a0 = __bfloat162float(ar_a[c_min]), a1 = __bfloat162float(ar_b[c_min]);
+        const int cw = c_min - c_lo_cur;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          const int kl = nt * 8 + t4 * 2;
+          const float b0 = __bfloat162float(bw[static_cast<long>(kl) * kRelBW + cw]);
+          const float b1 = __bfloat162float(bw[static_cast<long>(kl + 1) * kRelBW + cw]);
+          s[nt][0] += a0 + b0; s[nt][1] += a0 + b1; s[nt][2] += a1 + b0; s[nt][3] += a1 + b1;
+        }
+      } else {
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int kl = nt * 8 + t4 * 2 + (e & 1);
+            const int row = (e < 2) ? row_a : row_b;
+            // rows/keys of the padded tail of the last block fall outside the table: clamp (their scores are masked)
+            const int c = lut[min(max(row - key0 - kl, -p.lut_center), p.lut_center)];
+            const __nv_bfloat16* ar = (e < 2) ? ar_a : ar_b;
+            s[nt][e] += __bfloat162float(ar[c]) +
+                        __bfloat162float(bw[static_cast<long>(kl) * kRelBW + min(max(c - c_lo_cur, 0), kRelBW - 1)]);
+          }
+      }
+    }
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int key = key0 + nt * 8 + t4 * 2 + (e & 1);
         const int row = (e < 2) ? row_a : row_b;
-        float x = s[nt][e];
-        if (REL_BIAS) {
-          // rows/keys of the padded tail of the last block fall outside the table: clamp (their scores are masked)
-          const int c = p.bucket_lut[min(max(row - key, -p.lut_center), p.lut_center) + p.lut_center];
-          const __nv_bfloat16* ar = reinterpret_cast<const __nv_bfloat16*>(sA) + static_cast<long>(row - q0) * p.NB;
-          const __nv_bfloat16* br = reinterpret_cast<const __nv_bfloat16*>(sB + static_cast<long>(buf) * BN * kRelBW * 2) +
-                                    static_cast<long>(key - key0) * kRelBW;
-          x += __bfloat162float(ar[c]) + __bfloat162float(br[min(max(c - c_lo_cur, 0), kRelBW - 1)]);
-        }
-        x *= p.scale_log2;
         const bool dead = (key >= seq_len) || (CAUSAL && key > row);
-        s[nt][e] = dead ? -INFINITY : x;
+        s[nt][e] = dead ? -INFINITY : s[nt][e] * p.scale_log2;
       }
     // ---- online softmax (rows a = c0,c1 ; b = c2,c3) ----
     float mx[2] = {-INFINITY, -INFINITY};

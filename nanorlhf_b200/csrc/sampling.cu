@@ -15,9 +15,8 @@
 
 namespace nrl {
 
-constexpr int kSampThreads = 1024;
-constexpr int kBins = 2048;
-constexpr float kBinsPerOctave = 32.f;     // bin = floor(-log2(p) * 32), clamped: covers p down to 2^-64
+constexpr int kSampThreads = 512;       // 128 registers / thread: the 64 histogram accumulators stay in registers
+constexpr int kPerLane = kSampThreads / 32;
 
 template <typename T>
 struct RowVec;
@@ -66,6 +65,27 @@ NRL_DEVICE float block_reduce_max(float v, float* red) {
   return red[0];
 }
 
+// 64 accumulators reduced across the block; result broadcast in s_acc[0..63]
+NRL_DEVICE void block_reduce_64(float (&acc)[64], float* s_warp /* [32][64] */, float* s_acc /* [64] */) {
+#pragma unroll
+  for (int k = 0; k < 64; ++k) acc[k] = warp_sum(acc[k]);
+  __syncthreads();
+  if (lane_id() == 0) {
+#pragma unroll
+    for (int k = 0; k < 64; ++k) s_warp[(threadIdx.x >> 5) * 64 + k] = acc[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float t = 0.f;
+    for (int w = 0; w < (kSampThreads >> 5); ++w) t += s_warp[w * 64 + threadIdx.x];
+    s_acc[threadIdx.x] = t;
+  }
+  __syncthreads();
+}
+
+// Top-p by two-level (64 x 64) mass histograms held in REGISTERS (no shared-memory atomics): level 1 bins one
+// octave of probability each (relative to the row maximum), level 2 splits the octave that contains the
+// nucleus boundary into 64 slices, i.e. the cut-off probability is resolved to 2^(1/64) = 1.1 %.
 template <typename T>
 __global__ void __launch_bounds__(kSampThreads) sample_top_p_kernel(const T* __restrict__ logits, long row_stride,
                                                                     int V, float inv_temp, float top_p,
@@ -74,96 +94,91 @@ __global__ void __launch_bounds__(kSampThreads) sample_top_p_kernel(const T* __r
                                                                     const int* __restrict__ row_steps,
                                                                     int* __restrict__ out_tokens) {
   __shared__ float red[32];
-  __shared__ float hist[kBins];
+  __shared__ float s_warp[(kSampThreads / 32) * 64];
+  __shared__ float s_acc[64];
   __shared__ float chunk_sum[kSampThreads];
-  __shared__ int s_cut_bin;
-  __shared__ float s_kept_mass;
-  __shared__ int s_token;
+  __shared__ float s_thresh;
+  __shared__ float s_resid;
+  __shared__ int s_owner;
   const int row = blockIdx.x;
   const T* z = logits + static_cast<long>(row) * row_stride;
   const int tid = threadIdx.x;
-  // Thread t owns vectors t, t+1024, ... (coalesced 16-byte loads).  The categorical walk of pass 3 uses
-  // the fixed order "thread-major, then vector order" -- any fixed order is a valid sampling order.
   constexpr int VN = RowVec<T>::N;
   const int nvec = (V + VN - 1) / VN;
+  const float sc = inv_temp * 1.4426950408889634f;      // logits -> log2 domain
 
-  // ---- pass 1: max and sum-exp ----
+  // ---- pass 1: row maximum ----
   float mx = -INFINITY;
   for (int v = tid; v < nvec; v += kSampThreads) {
     float x[VN];
     RowVec<T>::load(z, v, x);
 #pragma unroll
     for (int j = 0; j < VN; ++j)
-      if (v * VN + j < V) mx = fmaxf(mx, x[j] * inv_temp);
+      if (v * VN + j < V) mx = fmaxf(mx, x[j] * sc);
   }
   mx = block_reduce_max(mx, red);
-  float se = 0.f;
-  for (int v = tid; v < nvec; v += kSampThreads) {
-    float x[VN];
-    RowVec<T>::load(z, v, x);
-#pragma unroll
-    for (int j = 0; j < VN; ++j)
-      if (v * VN + j < V) se += __expf(x[j] * inv_temp - mx);
-  }
-  se = block_reduce_sum(se, red);
-  const float inv_se = 1.f / se;
-  const float log2_inv_se = __log2f(inv_se);
 
-  // ---- pass 2: mass histogram ----
-  for (int i = tid; i < kBins; i += kSampThreads) hist[i] = 0.f;
-  __syncthreads();
-  {
-    // run-length aggregation: consecutive tokens of a thread that land in the same bin are summed in
-    // registers, so a flat distribution (random-init model) costs one shared atomic per thread, not 150
-    int cur_bin = -1;
-    float cur_mass = 0.f;
+  float thresh = INFINITY;                                // keep tokens with (mx - z) < thresh  [octaves below the max]
+  if (top_p < 1.f) {
+    // ---- pass 2: one-octave mass histogram ----
+    float acc[64];
+#pragma unroll
+    for (int k = 0; k < 64; ++k) acc[k] = 0.f;
     for (int v = tid; v < nvec; v += kSampThreads) {
       float x[VN];
       RowVec<T>::load(z, v, x);
 #pragma unroll
       for (int j = 0; j < VN; ++j)
         if (v * VN + j < V) {
-          float zl = x[j] * inv_temp - mx;                        // ln p = zl - ln(se)
-          float p = __expf(zl) * inv_se;
-          float nlog2 = -(zl * 1.4426950408889634f + log2_inv_se);
-          int b = min(kBins - 1, max(0, static_cast<int>(nlog2 * kBinsPerOctave)));
-          if (b != cur_bin) {
-            if (cur_bin >= 0) atomicAdd(&hist[cur_bin], cur_mass);
-            cur_bin = b;
-            cur_mass = 0.f;
-          }
-          cur_mass += p;
+          const float d = mx - x[j] * sc;
+          const float e = exp2f(-d);
+          const int b = min(63, static_cast<int>(d));
+#pragma unroll
+          for (int k = 0; k < 64; ++k) acc[k] += (b == k) ? e : 0.f;
         }
     }
-    if (cur_bin >= 0) atomicAdd(&hist[cur_bin], cur_mass);
-  }
-  __syncthreads();
-  if (tid < 32) {
-    // walk bins from the most probable; find the first bin where cumulative mass reaches top_p
-    float cum = 0.f;
-    int cut = kBins - 1;
-    bool found = false;
-    for (int base = 0; base < kBins && !found; base += 32) {
-      float incl = hist[base + tid];
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        float y = __shfl_up_sync(0xffffffffu, incl, o);
-        if (tid >= o) incl += y;
-      }
-      unsigned ball = __ballot_sync(0xffffffffu, cum + incl >= top_p);
-      if (ball) {
-        cut = base + __ffs(ball) - 1;
-        found = true;
-      } else {
-        cum += __shfl_sync(0xffffffffu, incl, 31);
-      }
+    block_reduce_64(acc, s_warp, s_acc);
+    float total = 0.f;
+    for (int k = 0; k < 64; ++k) total += s_acc[k];
+    const float target = top_p * total;
+    int B = 63;
+    float before = 0.f, cum = 0.f;
+    for (int k = 0; k < 64; ++k) {
+      if (cum + s_acc[k] >= target) { B = k; before = cum; break; }
+      cum += s_acc[k];
     }
-    if (tid == 0) s_cut_bin = cut;
+    __syncthreads();
+    // ---- pass 3: 1/64-octave histogram inside octave B ----
+#pragma unroll
+    for (int k = 0; k < 64; ++k) acc[k] = 0.f;
+    for (int v = tid; v < nvec; v += kSampThreads) {
+      float x[VN];
+      RowVec<T>::load(z, v, x);
+#pragma unroll
+      for (int j = 0; j < VN; ++j)
+        if (v * VN + j < V) {
+          const float d = mx - x[j] * sc;
+          const int b = min(63, static_cast<int>(d));
+          if (b == B) {
+            const float e = exp2f(-d);
+            const int f = min(63, static_cast<int>((d - static_cast<float>(B)) * 64.f));
+#pragma unroll
+            for (int k = 0; k < 64; ++k) acc[k] += (f == k) ? e : 0.f;
+          }
+        }
+    }
+    block_reduce_64(acc, s_warp, s_acc);
+    int Fc = 63;
+    cum = before;
+    for (int k = 0; k < 64; ++k) {
+      cum += s_acc[k];
+      if (cum >= target) { Fc = k; break; }
+    }
+    thresh = (B >= 63 && Fc >= 63) ? INFINITY : static_cast<float>(B) + static_cast<float>(Fc + 1) * (1.f / 64.f);
+    __syncthreads();
   }
-  __syncthreads();
-  const int cut_bin = s_cut_bin;
 
-  // ---- pass 3: draw and walk ----
+  // ---- pass 4: kept mass per thread (thread-major order), then draw and walk ----
   float mine = 0.f;
   for (int v = tid; v < nvec; v += kSampThreads) {
     float x[VN];
@@ -171,20 +186,17 @@ __global__ void __launch_bounds__(kSampThreads) sample_top_p_kernel(const T* __r
 #pragma unroll
     for (int j = 0; j < VN; ++j)
       if (v * VN + j < V) {
-        float zl = x[j] * inv_temp - mx;
-        float nlog2 = -(zl * 1.4426950408889634f + log2_inv_se);
-        int b = min(kBins - 1, max(0, static_cast<int>(nlog2 * kBinsPerOctave)));
-        if (b <= cut_bin) mine += __expf(zl) * inv_se;
+        const float d = mx - x[j] * sc;
+        if (d < thresh) mine += exp2f(-d);
       }
   }
   chunk_sum[tid] = mine;
   __syncthreads();
   if (tid < 32) {
-    // warp 0: prefix over the 1024 per-thread masses (32 each), pick the owner thread
-    float local[32];
+    float local[kPerLane];
     float tsum = 0.f;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) { local[i] = chunk_sum[tid * 32 + i]; tsum += local[i]; }
+    for (int i = 0; i < kPerLane; ++i) { local[i] = chunk_sum[tid * kPerLane + i]; tsum += local[i]; }
     float incl = tsum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -204,25 +216,25 @@ __global__ void __launch_bounds__(kSampThreads) sample_top_p_kernel(const T* __r
     unsigned ball = __ballot_sync(0xffffffffu, (incl >= u) && (tsum > 0.f));
     int wl = ball ? (__ffs(ball) - 1) : 31;
     if (tid == wl) {
-      float acc = excl;
-      int owner = tid * 32 + 31;
+      float acc2 = excl;
+      int owner = tid * kPerLane + kPerLane - 1;
       float resid = 0.f;
       bool hit = false;
-      for (int i = 0; i < 32; ++i) {
-        if (!hit && local[i] > 0.f && acc + local[i] >= u) { owner = tid * 32 + i; resid = u - acc; hit = true; }
-        if (!hit) acc += local[i];
+      for (int i = 0; i < kPerLane; ++i) {
+        if (!hit && local[i] > 0.f && acc2 + local[i] >= u) { owner = tid * kPerLane + i; resid = u - acc2; hit = true; }
+        if (!hit) acc2 += local[i];
       }
       if (!hit) {   // numerical slack: fall back to the last thread with mass
-        for (int i = 31; i >= 0; --i) if (local[i] > 0.f) { owner = tid * 32 + i; resid = local[i]; break; }
+        for (int i = kPerLane - 1; i >= 0; --i) if (local[i] > 0.f) { owner = tid * kPerLane + i; resid = local[i]; break; }
       }
-      s_token = owner;
-      s_kept_mass = resid;
+      s_owner = owner;
+      s_resid = resid;
     }
   }
   __syncthreads();
-  if (tid == s_token) {
-    const float resid = s_kept_mass;
-    float acc = 0.f;
+  if (tid == s_owner) {
+    const float resid = s_resid;
+    float acc2 = 0.f;
     int tok = -1, last_kept = -1;
     for (int v = tid; v < nvec && tok < 0; v += kSampThreads) {
       float x[VN];
@@ -230,13 +242,11 @@ __global__ void __launch_bounds__(kSampThreads) sample_top_p_kernel(const T* __r
 #pragma unroll
       for (int j = 0; j < VN; ++j)
         if (tok < 0 && v * VN + j < V) {
-          float zl = x[j] * inv_temp - mx;
-          float nlog2 = -(zl * 1.4426950408889634f + log2_inv_se);
-          int b = min(kBins - 1, max(0, static_cast<int>(nlog2 * kBinsPerOctave)));
-          if (b <= cut_bin) {
+          const float d = mx - x[j] * sc;
+          if (d < thresh) {
             last_kept = v * VN + j;
-            acc += __expf(zl) * inv_se;
-            if (acc >= resid) tok = v * VN + j;
+            acc2 += exp2f(-d);
+            if (acc2 >= resid) tok = v * VN + j;
           }
         }
     }
@@ -274,8 +284,9 @@ __global__ void __launch_bounds__(kSampThreads) argmax_kernel(const T* __restric
   if (lane_id() == 0) { s_val[threadIdx.x >> 5] = best; s_idx[threadIdx.x >> 5] = bi; }
   __syncthreads();
   if (threadIdx.x < 32) {
-    best = s_val[threadIdx.x];
-    bi = s_idx[threadIdx.x];
+    const bool has = threadIdx.x < (kSampThreads >> 5);
+    best = has ? s_val[threadIdx.x] : -INFINITY;
+    bi = has ? s_idx[threadIdx.x] : 0x7fffffff;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       float ov = __shfl_xor_sync(0xffffffffu, best, o);
