@@ -34,10 +34,10 @@ BASELINE_EPISODES_PER_S = 1.0      # reference README.md:36 "~1 s/episode" on 1 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--steps", type=int, default=1)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mini-batches", type=int, default=4,
+    ap.add_argument("--mini-batches", type=int, default=16,
                     help="num_mini_batches: prompts per rank per update = 4 x 8 x this (reference default 16 -> 512)")
     ap.add_argument("--response-length", type=int, default=1500)
     ap.add_argument("--samples", type=int, default=4)
@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--comm", default="fused", choices=["fused", "nccl"])
     ap.add_argument("--rollout-dtype", default="bf16")
     ap.add_argument("--reward", default="deberta-large", choices=["deberta-large", "deberta-tiny"])
+    ap.add_argument("--grad-checkpointing", type=int, default=0,
+                    help="1 = recompute activations like the reference (A100-40G memory saver); 0 = keep them (B200: 180 GB)")
     return ap.parse_args()
 
 
@@ -149,7 +151,7 @@ def main():
                      kl_coef=0.01, cliprange=0.2, per_device_train_batch_size=4, gradient_accumulation_steps=8,
                      num_mini_batches=args.mini_batches, num_ppo_epochs=1,
                      total_episodes=prompts_per_rank * comm.world_size * total_updates, learning_rate=6e-6,
-                     gradient_checkpointing=True, save_strategy="no", report_to="none", sampler="native",
+                     gradient_checkpointing=bool(args.grad_checkpointing), save_strategy="no", report_to="none", sampler="native",
                      rollout_dtype=args.rollout_dtype, comm=args.comm, resume="never", grpo_sample_N=args.samples,
                      watchdog_timeout_s=0)
     cfg.quiet = True
@@ -210,6 +212,7 @@ def main():
                        "global_batch": prompts_per_rank * comm.world_size, "samples_per_prompt": args.samples,
                        "seq_len": args.response_length, "prompt_len": "24-160", "parallelism": f"dp{comm.world_size}",
                        "comm": args.comm if comm.world_size > 1 else "none", "rollout_dtype": args.rollout_dtype,
+                       "gradient_checkpointing": bool(args.grad_checkpointing),
                        "l2_policy": "working set (3 GB weights + KV pages + activations) exceeds the 126 MB L2 every step"},
             "e2e": {"value": e2e, "unit": "episodes/s", "h2d_bytes_per_step": (trainer.io_bytes["h2d"] - h2d0) / args.steps,
                     "d2h_bytes_per_step": (trainer.io_bytes["d2h"] - d2h0) / args.steps},

@@ -1,11 +1,11 @@
 // K5 sampler: temperature + nucleus (top-p) + seeded categorical draw, or arg-max at temperature 0.
 //
-// One CTA per sequence, three streaming passes over the row of logits (never sorted, never copied):
-//   1. online max / sum-exp                                   -> softmax normaliser
-//   2. probability-mass histogram over 2048 log2-spaced bins  -> top-p threshold bin (mass from the top)
-//   3. draw u ~ Philox(seed, row, step) in [0, kept mass) and walk the kept tokens in index order
-// The kept set is {p >= lower edge of the threshold bin}: the smallest probability kept is within one
-// bin width (2^(1/32) - 1 = 2.2 %) of the exact top-p cut-off.
+// One CTA per sequence, four streaming passes over the row of logits (never sorted, never copied):
+//   1. row maximum
+//   2. probability-mass histogram, one bin per octave below the maximum   -> octave holding the top-p boundary
+//   3. 64-slice histogram inside that octave                              -> cut-off resolved to 2^(1/64) = 1.1 %
+//   4. kept mass per thread; draw u ~ Philox(seed, row, step) in (0, kept mass] and walk the kept tokens
+// Histograms are lane-private shared-memory columns ([bin][lane]: bank == lane), so there are no atomics.
 // Reference: vLLM SamplingParams(temperature, top_p=0.95, seed=...) in vllm_generate
 // (/root/reference/GRPO/grpo_trainer.py:127) and the T=0 greedy pass of ReMax (remax_trainer.py:167).
 #include <curand_kernel.h>
@@ -15,7 +15,7 @@
 
 namespace nrl {
 
-constexpr int kSampThreads = 512;       // 128 registers / thread: the 64 histogram accumulators stay in registers
+constexpr int kSampThreads = 256;       // 8 warps x 8 KB private histograms = 64 KB: 3 CTAs (rows) per SM
 constexpr int kPerLane = kSampThreads / 32;
 
 template <typename T>
@@ -65,27 +65,29 @@ NRL_DEVICE float block_reduce_max(float v, float* red) {
   return red[0];
 }
 
-// 64 accumulators reduced across the block; result broadcast in s_acc[0..63]
-NRL_DEVICE void block_reduce_64(float (&acc)[64], float* s_warp /* [32][64] */, float* s_acc /* [64] */) {
-#pragma unroll
-  for (int k = 0; k < 64; ++k) acc[k] = warp_sum(acc[k]);
+// Top-p by two-level (64 x 64) mass histograms with NO atomics: every lane owns a private column of a
+// per-warp shared-memory histogram laid out [bin][lane] (bank == lane: conflict-free read-modify-write).
+// Level 1 bins one octave of probability each (relative to the row maximum); level 2 splits the octave that
+// contains the nucleus boundary into 64 slices, so the cut-off probability is resolved to 2^(1/64) = 1.1 %.
+NRL_DEVICE void hist_clear(float* h) {
+  for (int i = threadIdx.x; i < (kSampThreads / 32) * 64 * 32; i += kSampThreads) h[i] = 0.f;
   __syncthreads();
-  if (lane_id() == 0) {
-#pragma unroll
-    for (int k = 0; k < 64; ++k) s_warp[(threadIdx.x >> 5) * 64 + k] = acc[k];
-  }
+}
+// sum the private columns: result in s_acc[0..63]
+NRL_DEVICE void hist_reduce(const float* h, float* s_acc) {
   __syncthreads();
-  if (threadIdx.x < 64) {
-    float t = 0.f;
-    for (int w = 0; w < (kSampThreads >> 5); ++w) t += s_warp[w * 64 + threadIdx.x];
-    s_acc[threadIdx.x] = t;
-  }
+  // 64 bins x (warps*32) columns; thread t handles bin t/4 (kSampThreads = 256 -> 4 threads per bin)
+  constexpr int TPB = kSampThreads / 64;
+  const int bin = threadIdx.x / TPB, part = threadIdx.x % TPB;
+  float t = 0.f;
+  for (int w = 0; w < kSampThreads / 32; ++w)
+    for (int l = part; l < 32; l += TPB) t += h[(w * 64 + bin) * 32 + l];
+#pragma unroll
+  for (int o = TPB / 2; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  if (part == 0) s_acc[bin] = t;
   __syncthreads();
 }
 
-// Top-p by two-level (64 x 64) mass histograms held in REGISTERS (no shared-memory atomics): level 1 bins one
-// octave of probability each (relative to the row maximum), level 2 splits the octave that contains the
-// nucleus boundary into 64 slices, i.e. the cut-off probability is resolved to 2^(1/64) = 1.1 %.
 template <typename T>
 __global__ void __launch_bounds__(kSampThreads) sample_top_p_kernel(const T* __restrict__ logits, long row_stride,
                                                                     int V, float inv_temp, float top_p,
@@ -93,11 +95,10 @@ __global__ void __launch_bounds__(kSampThreads) sample_top_p_kernel(const T* __r
                                                                     const int* __restrict__ row_ids,
                                                                     const int* __restrict__ row_steps,
                                                                     int* __restrict__ out_tokens) {
+  extern __shared__ float s_hist[];                      // [warps][64][32]
   __shared__ float red[32];
-  __shared__ float s_warp[(kSampThreads / 32) * 64];
   __shared__ float s_acc[64];
   __shared__ float chunk_sum[kSampThreads];
-  __shared__ float s_thresh;
   __shared__ float s_resid;
   __shared__ int s_owner;
   const int row = blockIdx.x;
@@ -106,6 +107,7 @@ __global__ void __launch_bounds__(kSampThreads) sample_top_p_kernel(const T* __r
   constexpr int VN = RowVec<T>::N;
   const int nvec = (V + VN - 1) / VN;
   const float sc = inv_temp * 1.4426950408889634f;      // logits -> log2 domain
+  float* my_hist = s_hist + (tid >> 5) * 64 * 32 + (tid & 31);
 
   // ---- pass 1: row maximum ----
   float mx = -INFINITY;
@@ -121,9 +123,7 @@ __global__ void __launch_bounds__(kSampThreads) sample_top_p_kernel(const T* __r
   float thresh = INFINITY;                                // keep tokens with (mx - z) < thresh  [octaves below the max]
   if (top_p < 1.f) {
     // ---- pass 2: one-octave mass histogram ----
-    float acc[64];
-#pragma unroll
-    for (int k = 0; k < 64; ++k) acc[k] = 0.f;
+    hist_clear(s_hist);
     for (int v = tid; v < nvec; v += kSampThreads) {
       float x[VN];
       RowVec<T>::load(z, v, x);
@@ -131,13 +131,11 @@ __global__ void __launch_bounds__(kSampThreads) sample_top_p_kernel(const T* __r
       for (int j = 0; j < VN; ++j)
         if (v * VN + j < V) {
           const float d = mx - x[j] * sc;
-          const float e = exp2f(-d);
           const int b = min(63, static_cast<int>(d));
-#pragma unroll
-          for (int k = 0; k < 64; ++k) acc[k] += (b == k) ? e : 0.f;
+          my_hist[b * 32] += exp2f(-d);
         }
     }
-    block_reduce_64(acc, s_warp, s_acc);
+    hist_reduce(s_hist, s_acc);
     float total = 0.f;
     for (int k = 0; k < 64; ++k) total += s_acc[k];
     const float target = top_p * total;
@@ -149,8 +147,7 @@ __global__ void __launch_bounds__(kSampThreads) sample_top_p_kernel(const T* __r
     }
     __syncthreads();
     // ---- pass 3: 1/64-octave histogram inside octave B ----
-#pragma unroll
-    for (int k = 0; k < 64; ++k) acc[k] = 0.f;
+    hist_clear(s_hist);
     for (int v = tid; v < nvec; v += kSampThreads) {
       float x[VN];
       RowVec<T>::load(z, v, x);
@@ -160,14 +157,12 @@ __global__ void __launch_bounds__(kSampThreads) sample_top_p_kernel(const T* __r
           const float d = mx - x[j] * sc;
           const int b = min(63, static_cast<int>(d));
           if (b == B) {
-            const float e = exp2f(-d);
             const int f = min(63, static_cast<int>((d - static_cast<float>(B)) * 64.f));
-#pragma unroll
-            for (int k = 0; k < 64; ++k) acc[k] += (f == k) ? e : 0.f;
+            my_hist[f * 32] += exp2f(-d);
           }
         }
     }
-    block_reduce_64(acc, s_warp, s_acc);
+    hist_reduce(s_hist, s_acc);
     int Fc = 63;
     cum = before;
     for (int k = 0; k < 64; ++k) {
@@ -313,11 +308,18 @@ extern "C" cudaError_t nrl_sample(const void* logits, int is_bf16, long row_stri
   } else {
     float inv_t = 1.f / temperature;
     if (top_p >= 1.f) top_p = 2.f;     // keep everything
+    const int hist_bytes = (kSampThreads / 32) * 64 * 32 * 4;
+    static bool configured = false;
+    if (!configured) {
+      cudaFuncSetAttribute(sample_top_p_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, hist_bytes);
+      cudaFuncSetAttribute(sample_top_p_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, hist_bytes);
+      configured = true;
+    }
     if (is_bf16)
-      sample_top_p_kernel<__nv_bfloat16><<<rows, kSampThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(logits), row_stride, V,
+      sample_top_p_kernel<__nv_bfloat16><<<rows, kSampThreads, hist_bytes, s>>>(static_cast<const __nv_bfloat16*>(logits), row_stride, V,
                                                                        inv_t, top_p, seed, step, row_ids, row_steps, out_tokens);
     else
-      sample_top_p_kernel<float><<<rows, kSampThreads, 0, s>>>(static_cast<const float*>(logits), row_stride, V, inv_t,
+      sample_top_p_kernel<float><<<rows, kSampThreads, hist_bytes, s>>>(static_cast<const float*>(logits), row_stride, V, inv_t,
                                                                top_p, seed, step, row_ids, row_steps, out_tokens);
   }
   return cudaGetLastError();
