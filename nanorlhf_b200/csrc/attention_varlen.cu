@@ -312,6 +312,173 @@ __global__ void __launch_bounds__(128) flash_fwd_kernel(AttnParams p) {
   }
 }
 
+// Causal forward with TWO 16-row MMA tiles per warp (BM = 128): every K / V fragment fetched with ldmatrix feeds two
+// MMAs instead of one, which moves the kernel from shared-memory-bandwidth bound to tensor-pipe bound.
+template <int D, int BN>
+__global__ void __launch_bounds__(128) flash_fwd_causal_mt2_kernel(AttnParams p) {
+  constexpr int BM = 128, KS = D / 16, NT = BN / 8, MT = 2;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sQ = smem;                              // [128][D]
+  uint8_t* sK = sQ + BM * D * 2;                   // [2][BN][D]
+  uint8_t* sV = sK + 2 * BN * D * 2;               // [2][BN][D]
+
+  int seq, m_blk, seq_start, seq_len;
+  if (!locate_block<BM>(p.cu_seqlens, p.num_seqs, blockIdx.x, seq, m_blk, seq_start, seq_len)) return;
+  const int head = blockIdx.y, kvh = head / p.G;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
+  const int q0 = m_blk * BM;
+  const int n_blocks = min((seq_len + BN - 1) / BN, (q0 + BM + BN - 1) / BN);
+  const __nv_bfloat16* qbase = p.q + static_cast<long>(seq_start) * p.q_stride_t;
+  const __nv_bfloat16* kbase = p.k + static_cast<long>(seq_start) * p.k_stride_t;
+  const __nv_bfloat16* vbase = p.v + static_cast<long>(seq_start) * p.v_stride_t;
+
+  load_tile_async<D, BM, 128>(sQ, qbase, p.q_stride_t, head, q0, seq_len);
+  auto load_kv = [&](int nb, int buf) {
+    load_tile_async<D, BN, 128>(sK + buf * BN * D * 2, kbase, p.k_stride_t, kvh, nb * BN, seq_len);
+    load_tile_async<D, BN, 128>(sV + buf * BN * D * 2, vbase, p.v_stride_t, kvh, nb * BN, seq_len);
+  };
+  load_kv(0, 0);
+  cp_async_commit();
+
+  float o[MT][D / 8][4];
+  float m_run[MT][2], l_run[MT][2];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+    for (int i = 0; i < D / 8; ++i) o[mt][i][0] = o[mt][i][1] = o[mt][i][2] = o[mt][i][3] = 0.f;
+    m_run[mt][0] = m_run[mt][1] = -INFINITY;
+    l_run[mt][0] = l_run[mt][1] = 0.f;
+  }
+  const int wrow0 = q0 + warp * 32;                 // first query row of this warp
+  const uint32_t qb = smem_u32(sQ);
+
+  for (int nb = 0; nb < n_blocks; ++nb) {
+    const int buf = nb & 1;
+    if (nb + 1 < n_blocks) load_kv(nb + 1, buf ^ 1);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    const int key0 = nb * BN;
+    if (key0 <= wrow0 + 31) {                        // causal: later key blocks are fully masked for this warp
+      const uint32_t kb = smem_u32(sK + buf * BN * D * 2), vb = smem_u32(sV + buf * BN * D * 2);
+      float s[MT][NT][4];
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int i = 0; i < NT; ++i) s[mt][i][0] = s[mt][i][1] = s[mt][i][2] = s[mt][i][3] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        uint32_t qf[MT][4];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          const int mrow = warp * 32 + mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, mcol = lane >> 4;
+          ldsm_x4(qf[mt], qb + tile_off<D>(mrow, ks * 2 + mcol));
+        }
+#pragma unroll
+        for (int np = 0; np < NT / 2; ++np) {
+          uint32_t kf[4];
+          const int mrow = np * 16 + (lane & 7) + (lane >> 4) * 8, mcol = (lane >> 3) & 1;
+          ldsm_x4(kf, kb + tile_off<D>(mrow, ks * 2 + mcol));
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            mma16816(s[mt][np * 2], qf[mt], kf[0], kf[1]);
+            mma16816(s[mt][np * 2 + 1], qf[mt], kf[2], kf[3]);
+          }
+        }
+      }
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        const int row_a = wrow0 + mt * 16 + g, row_b = row_a + 8;
+        float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int key = key0 + nt * 8 + t4 * 2 + (e & 1);
+            const int row = (e < 2) ? row_a : row_b;
+            const bool dead = (key >= seq_len) || (key > row);
+            const float x = dead ? -INFINITY : s[mt][nt][e] * p.scale_log2;
+            s[mt][nt][e] = x;
+            mx[e >> 1] = fmaxf(mx[e >> 1], x);
+          }
+        float corr[2], ps[2] = {0.f, 0.f};
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+          mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+          const float mn = fmaxf(m_run[mt][r], mx[r]);
+          corr[r] = (mn == -INFINITY) ? 1.f : exp2f(m_run[mt][r] - mn);
+          m_run[mt][r] = mn;
+        }
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int r = e >> 1;
+            const float pv = (m_run[mt][r] == -INFINITY) ? 0.f : exp2f(s[mt][nt][e] - m_run[mt][r]);
+            s[mt][nt][e] = pv;
+            ps[r] += pv;
+          }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          ps[r] += __shfl_xor_sync(0xffffffffu, ps[r], 1);
+          ps[r] += __shfl_xor_sync(0xffffffffu, ps[r], 2);
+          l_run[mt][r] = l_run[mt][r] * corr[r] + ps[r];
+        }
+#pragma unroll
+        for (int i = 0; i < D / 8; ++i) {
+          o[mt][i][0] *= corr[0]; o[mt][i][1] *= corr[0]; o[mt][i][2] *= corr[1]; o[mt][i][3] *= corr[1];
+        }
+      }
+#pragma unroll
+      for (int ks = 0; ks < BN / 16; ++ks) {
+        uint32_t pa[MT][4];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          pa[mt][0] = pack_bf16x2(s[mt][2 * ks][0], s[mt][2 * ks][1]);
+          pa[mt][1] = pack_bf16x2(s[mt][2 * ks][2], s[mt][2 * ks][3]);
+          pa[mt][2] = pack_bf16x2(s[mt][2 * ks + 1][0], s[mt][2 * ks + 1][1]);
+          pa[mt][3] = pack_bf16x2(s[mt][2 * ks + 1][2], s[mt][2 * ks + 1][3]);
+        }
+#pragma unroll
+        for (int nd = 0; nd < D / 16; ++nd) {
+          uint32_t vf[4];
+          const int mrow = ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, mcol = lane >> 4;
+          ldsm_x4_t(vf, vb + tile_off<D>(mrow, nd * 2 + mcol));
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            mma16816(o[mt][nd * 2], pa[mt], vf[0], vf[1]);
+            mma16816(o[mt][nd * 2 + 1], pa[mt], vf[2], vf[3]);
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  cp_async_wait<0>();
+
+  __nv_bfloat16* obase = p.out + static_cast<long>(seq_start) * p.o_stride_t + head * D;
+  const float ln2 = 0.6931471805599453f;
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) {
+    const int row_a = wrow0 + mt * 16 + g, row_b = row_a + 8;
+    const float inv_a = l_run[mt][0] > 0.f ? 1.f / l_run[mt][0] : 0.f, inv_b = l_run[mt][1] > 0.f ? 1.f / l_run[mt][1] : 0.f;
+#pragma unroll
+    for (int i = 0; i < D / 8; ++i) {
+      const int col = i * 8 + t4 * 2;
+      if (row_a < seq_len)
+        *reinterpret_cast<uint32_t*>(obase + static_cast<long>(row_a) * p.o_stride_t + col) = pack_bf16x2(o[mt][i][0] * inv_a, o[mt][i][1] * inv_a);
+      if (row_b < seq_len)
+        *reinterpret_cast<uint32_t*>(obase + static_cast<long>(row_b) * p.o_stride_t + col) = pack_bf16x2(o[mt][i][2] * inv_b, o[mt][i][3] * inv_b);
+    }
+    if (p.lse != nullptr && t4 == 0) {
+      float* lse = p.lse + static_cast<long>(head) * p.total_tokens + seq_start;
+      if (row_a < seq_len) lse[row_a] = (m_run[mt][0] + log2f(l_run[mt][0])) * ln2;
+      if (row_b < seq_len) lse[row_b] = (m_run[mt][1] + log2f(l_run[mt][1])) * ln2;
+    }
+  }
+}
+
 // =================================================================================================
 // backward
 // =================================================================================================
@@ -640,10 +807,12 @@ extern "C" cudaError_t nrl_attn_varlen_fwd(const void* q, const void* k, const v
     if ((e = set_smem(kern, smem)) != cudaSuccess) return e;
     kern<<<grid, 128, smem, s>>>(p);
   } else if (D == 128 && causal) {
-    const int smem = 64 * 128 * 2 + 4 * 64 * 128 * 2;
-    auto kern = flash_fwd_kernel<128, true, false, 64>;
+    constexpr int BN = 32;
+    const int smem = 128 * 128 * 2 + 4 * BN * 128 * 2;
+    auto kern = flash_fwd_causal_mt2_kernel<128, BN>;
     if ((e = set_smem(kern, smem)) != cudaSuccess) return e;
-    kern<<<grid, 128, smem, s>>>(p);
+    dim3 grid2(total / 128 + num_seqs, Hq);
+    kern<<<grid2, 128, smem, s>>>(p);
   } else if (D == 64 && causal) {
     const int smem = 64 * 64 * 2 + 4 * 64 * 64 * 2;
     auto kern = flash_fwd_kernel<64, true, false, 64>;
