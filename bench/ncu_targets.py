@@ -1,0 +1,44 @@
+"""Tiny driver for `ncu --set full`: one launch each of the headline kernels at bench shapes."""
+import math
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from nanorlhf_b200.ops import native  # noqa: E402
+
+native.load()
+dev = "cuda"
+which = sys.argv[1] if len(sys.argv) > 1 else "all"
+torch.manual_seed(0)
+if which in ("all", "gemm"):
+    a = torch.randn(2048, 1536, device=dev, dtype=torch.bfloat16)
+    b = torch.randn(17920, 1536, device=dev, dtype=torch.bfloat16)
+    for _ in range(3):
+        native.gemm_bf16(a, b)
+if which in ("all", "lmhead"):
+    h = torch.randn(8192, 1536, device=dev, dtype=torch.bfloat16)
+    w = (torch.randn(151936, 1536, device=dev) * 0.02).bfloat16()
+    t = torch.randint(0, 151936, (8192,), device=dev, dtype=torch.int32)
+    for _ in range(2):
+        native.ext().lmhead_logprob_fwd(h, w, t, 1 / 0.9, 0)
+if which in ("all", "decode"):
+    S, ctx, Hq, Hkv, D = 2048, 1000, 12, 2, 128
+    per = ctx // 16 + 1
+    kc = torch.randn(S * per, Hkv, 16, D, device=dev, dtype=torch.bfloat16)
+    vc = torch.randn_like(kc)
+    bt = torch.arange(S * per, device=dev, dtype=torch.int32).view(S, per)
+    cl = torch.full((S,), ctx, device=dev, dtype=torch.int32)
+    q = torch.randn(S, Hq, D, device=dev, dtype=torch.bfloat16)
+    for _ in range(3):
+        native.paged_decode(q, kc, vc, bt, cl)
+if which in ("all", "attn"):
+    T = 4 * 1650
+    cu = torch.tensor([0, 1650, 3300, 4950, 6600], device=dev, dtype=torch.int32)
+    q = torch.randn(T, 12, 128, device=dev, dtype=torch.bfloat16)
+    k = torch.randn(T, 2, 128, device=dev, dtype=torch.bfloat16)
+    v = torch.randn(T, 2, 128, device=dev, dtype=torch.bfloat16)
+    for _ in range(2):
+        native.ext().attn_varlen_fwd(q, k, v, cu, 1650, 1 / math.sqrt(128), True)
+torch.cuda.synchronize()
