@@ -69,3 +69,76 @@ def refresh_layer(sampler, li: int):
 def refresh_sampler_arena(sampler):
     for li in range(sampler.cfg.num_hidden_layers):
         refresh_layer(sampler, li)
+
+
+# ------------------------------------------------------------------------------------------------
+# data-parallel variant: layer-sharded merge + peer stores over NVLink
+# ------------------------------------------------------------------------------------------------
+class ShardedWeightSync:
+    """K-BC across ranks: rank r merges (W + (alpha/r) B A) only for layers with ``layer % world == r`` and the
+    GEMM epilogue's TMA stores land directly in *every* rank's sampler arena (the arenas live in symmetric
+    memory, so a peer's arena is an ordinary global address over NVLink).  Per rank: 1/world of the merge
+    math and HBM reads, (world-1)/world of the arena arrives over NVLink instead of being recomputed.
+
+    Measured trade-off: when every rank already holds the full training weights a
+    *local* merge moves fewer bytes than receiving merged weights over NVLink, so ``refresh_sampler_arena``
+    stays the default; this path is for configurations where the merge inputs are sharded.
+    """
+
+    def __init__(self, sampler, comm):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        self.sampler, self.comm = sampler, comm
+        self.symm_mem, self.group = symm_mem, dist.group.WORLD
+        cfg = sampler.cfg
+        D = cfg.head_dim
+        nq, nkv, F, d = cfg.num_attention_heads * D, cfg.num_key_value_heads * D, cfg.intermediate_size, cfg.hidden_size
+        self.shapes = [("wqkv", (nq + 2 * nkv, d)), ("wo", (d, nq)), ("wgu", (2 * F, d)), ("wdown", (d, F))]
+        per_layer = sum(a * b for _, (a, b) in self.shapes)
+        self.per_layer = per_layer
+        self.flat = symm_mem.empty(per_layer * cfg.num_hidden_layers, dtype=torch.bfloat16, device=sampler.device)
+        self.hdl = symm_mem.rendezvous(self.flat, self.group.group_name)
+        # re-point the sampler's arena at the symmetric buffer
+        for li, lw in enumerate(sampler.layers):
+            off = li * per_layer
+            for name, (a, b) in self.shapes:
+                getattr(lw, name)  # must exist
+                setattr(lw, name, self.flat[off:off + a * b].view(a, b))
+                off += a * b
+
+    def _peer_view(self, peer: int, li: int, name: str):
+        off = li * self.per_layer
+        for n, (a, b) in self.shapes:
+            if n == name:
+                return self.hdl.get_buffer(peer, (a, b), torch.bfloat16, off)
+            off += a * b
+        raise KeyError(name)
+
+    @torch.no_grad()
+    def refresh(self):
+        s, W, R = self.sampler, self.comm.world_size, self.comm.rank
+        cfg = s.cfg
+        D = cfg.head_dim
+        nq, nkv, F = cfg.num_attention_heads * D, cfg.num_key_value_heads * D, cfg.intermediate_size
+        self.hdl.barrier(channel=0)                         # nobody is still sampling from the old arena
+        for li in range(cfg.num_hidden_layers):
+            layer, lw = s.lm.model.layers[li], s.layers[li]
+            at, mlp = layer.self_attn, layer.mlp
+            if li % W == R:
+                for peer in range(W):
+                    wqkv = self._peer_view(peer, li, "wqkv")
+                    _merged(at.q_proj, wqkv[:nq])
+                    _merged(at.k_proj, wqkv[nq:nq + nkv])
+                    _merged(at.v_proj, wqkv[nq + nkv:])
+                    _merged(at.o_proj, self._peer_view(peer, li, "wo"))
+                    wgu = self._peer_view(peer, li, "wgu")
+                    _merged(mlp.gate_proj, wgu[:F])
+                    _merged(mlp.up_proj, wgu[F:])
+                    _merged(mlp.down_proj, self._peer_view(peer, li, "wdown"))
+            # biases / norms are tiny and replicated: local copies
+            for mod, sl in ((at.q_proj, slice(0, nq)), (at.k_proj, slice(nq, nq + nkv)), (at.v_proj, slice(nq + nkv, nq + 2 * nkv))):
+                b = _bias(mod)
+                if b is not None:
+                    lw.bqkv[sl].copy_(b)
+            lw.ln1, lw.ln2 = layer.input_layernorm.weight, layer.post_attention_layernorm.weight
+        self.hdl.barrier(channel=1)                         # every peer's stores have landed
