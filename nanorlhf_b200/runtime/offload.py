@@ -106,8 +106,9 @@ class TieringEngine:
     def _make_role(self, name, tensors, residency, dirty, rebinder):
         r = _Role(name, tensors, residency, dirty, rebinder)
         flat = torch.empty(r.total, dtype=r.dtype, device=self.device)
-        for v, t in zip(r.views(flat), tensors):
-            v.copy_(t)
+        with torch.no_grad():
+            for v, t in zip(r.views(flat), tensors):
+                v.copy_(t.detach())
         r.dev = flat
         rebinder(r.views(flat))
         r.host = torch.empty(r.total, dtype=r.dtype, pin_memory=True)
