@@ -72,6 +72,26 @@ torch::Tensor gemm_bf16(const torch::Tensor& a, const torch::Tensor& b, const c1
   return out;
 }
 
+// act[M, F] = silu(x Wg^T) * (x Wu^T) with W_gu_interleaved[2F, K] (rows: per 32 features [32 gate | 32 up])
+torch::Tensor gemm_swiglu(const torch::Tensor& a, const torch::Tensor& w_interleaved, c10::optional<torch::Tensor> out_opt) {
+  check_bf16_2d(a, "a");
+  check_bf16_2d(w_interleaved, "w");
+  const int64_t M = a.size(0), K = a.size(1), N2 = w_interleaved.size(0);
+  TORCH_CHECK(w_interleaved.size(1) == K && N2 % 128 == 0 && K % 8 == 0, "2F must be a multiple of 128");
+  c10::cuda::CUDAGuard guard(a.device());
+  torch::Tensor out = out_opt.has_value() ? *out_opt : torch::empty({M, N2 / 2}, a.options());
+  check_bf16_2d(out, "out");
+  if (M == 0) return out;
+  const int bn = pick_block_n(M, N2);
+  CUtensorMap tmA = nrl::make_tma_2d(a.data_ptr(), M, K, a.stride(0) * 2, 128, 64, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2);
+  CUtensorMap tmB = nrl::make_tma_2d(w_interleaved.data_ptr(), N2, K, w_interleaved.stride(0) * 2, bn, 64, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2);
+  CUtensorMap tmD = nrl::make_tma_2d(out.data_ptr(), M, N2 / 2, out.stride(0) * 2, 128, 64, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2);
+  nrl::GemmParams p{};
+  p.M = M; p.N = N2; p.K = K; p.n_splits = 1; p.scale = 1.f;
+  check(nrl_gemm_bf16_tn(&tmA, &tmB, &tmD, &p, bn, nrl::EPI_SWIGLU, num_sms(), cur_stream()), "gemm_swiglu");
+  return out;
+}
+
 int pick_splits(int64_t M, int64_t N, int bn) {
   int64_t num_m = (M + 127) / 128, num_n = (N + bn - 1) / bn;
   int64_t s = (num_sms() + num_m - 1) / num_m;       // enough work items to cover the SMs
@@ -481,6 +501,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("inv_temperature"), py::arg("n_splits") = 0);
   m.def("lmhead_dlogits", &lmhead_dlogits);
   m.def("lora_merge", &lora_merge);
+  m.def("gemm_swiglu", &gemm_swiglu, py::arg("a"), py::arg("w_interleaved"), py::arg("out") = py::none());
   m.def("rmsnorm", &rmsnorm, py::arg("x"), py::arg("w"), py::arg("eps"), py::arg("residual") = py::none(),
         py::arg("want_rstd") = false);
   m.def("rmsnorm_bwd", &rmsnorm_bwd);

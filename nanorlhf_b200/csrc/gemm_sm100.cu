@@ -13,6 +13,7 @@
 //   EPI_STORE   bf16 store (+ optional bias[N]) through swizzled smem + TMA store           (K3: linear layers)
 //   EPI_LOGPROB fused lm-head log-prob (K-LP fwd): per-row online (max, sum-exp, sum exp*z) over the vocab
 //               range of the work item + target logit; nothing of size [M,V] is ever written
+//   EPI_SWIGLU  gate_up projection with silu(gate)*up applied in the epilogue (interleaved weight rows)
 //   EPI_DLOGITS K-LP backward: dZ = (onehot(target) - softmax(z)) * g / T in bf16 via TMA store
 //
 // Reference call sites this replaces: cuBLAS GEMMs behind every nn.Linear and the
@@ -217,6 +218,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
         const uint32_t t_acc = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(quad * 32) << 16);
+        uint32_t swiglu_packed[32];
+        (void)swiglu_packed;
 #pragma unroll 1
         for (int c = 0; c < BLOCK_N / 64; ++c) {
           uint32_t v[2][32];
@@ -261,6 +264,39 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                   run_ez = fmaf(e, (z == -INFINITY) ? 0.f : z, run_ez);
                 }
               run_max = new_max;
+            }
+          } else if (EPI == EPI_SWIGLU) {
+            // ---- fused SwiGLU: the weight rows are interleaved so that every 64-column chunk of the tile is
+            //      [32 gate | 32 up] of the same 32 features; two chunks make one 64-wide output slab ----
+            uint32_t cur[16];
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              const float g0 = __uint_as_float(v[0][j]), g1 = __uint_as_float(v[0][j + 1]);
+              const float u0 = __uint_as_float(v[1][j]), u1 = __uint_as_float(v[1][j + 1]);
+              cur[j / 2] = pack_bf16x2(g0 / (1.f + exp2f(-g0 * kLog2e)) * u0, g1 / (1.f + exp2f(-g1 * kLog2e)) * u1);
+            }
+            if ((c & 1) == 0) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) swiglu_packed[j] = cur[j];
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) swiglu_packed[16 + j] = cur[j];
+              uint8_t* buf = staging + store_buf * kStagingBytes;
+              if (epi_tid == 0) tma_store_wait_read<1>();
+              named_barrier_sync(1, kNumEpiThreads);
+              uint8_t* rowp = buf + row_in_tile * 128;
+#pragma unroll
+              for (int ch = 0; ch < 8; ++ch) {
+                uint4 q = make_uint4(swiglu_packed[ch * 4], swiglu_packed[ch * 4 + 1], swiglu_packed[ch * 4 + 2], swiglu_packed[ch * 4 + 3]);
+                *reinterpret_cast<uint4*>(rowp + ((ch ^ (row_in_tile & 7)) * 16)) = q;
+              }
+              fence_proxy_async_smem();
+              named_barrier_sync(2, kNumEpiThreads);
+              if (epi_tid == 0) {
+                tma_store_2d(&tmD, buf, n_blk * (BLOCK_N / 2) + (c >> 1) * 64, m_blk * BLOCK_M);
+                tma_store_commit();
+              }
+              store_buf ^= 1;
             }
           } else {
             // ---- bf16 tile store through swizzled smem + TMA ----
@@ -392,7 +428,9 @@ extern "C" cudaError_t nrl_gemm_bf16_tn(const CUtensorMap* tmA, const CUtensorMa
     if (epi == EPI_LOGPROB) return launch_impl<256, EPI_LOGPROB>(*tmA, *tmB, *tmD, *p, num_sms, stream);
     if (epi == EPI_DLOGITS) return launch_impl<256, EPI_DLOGITS>(*tmA, *tmB, *tmD, *p, num_sms, stream);
     if (epi == EPI_MERGE) return launch_impl<256, EPI_MERGE>(*tmA, *tmB, *tmD, *p, num_sms, stream);
+    if (epi == EPI_SWIGLU) return launch_impl<256, EPI_SWIGLU>(*tmA, *tmB, *tmD, *p, num_sms, stream);
   } else if (block_n == 128) {
+    if (epi == EPI_SWIGLU) return launch_impl<128, EPI_SWIGLU>(*tmA, *tmB, *tmD, *p, num_sms, stream);
     if (epi == EPI_MERGE) return launch_impl<128, EPI_MERGE>(*tmA, *tmB, *tmD, *p, num_sms, stream);
     if (epi == EPI_STORE) return launch_impl<128, EPI_STORE>(*tmA, *tmB, *tmD, *p, num_sms, stream);
     if (epi == EPI_LOGPROB) return launch_impl<128, EPI_LOGPROB>(*tmA, *tmB, *tmD, *p, num_sms, stream);

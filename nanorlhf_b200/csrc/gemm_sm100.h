@@ -10,6 +10,7 @@ enum GemmEpilogue : int {
   EPI_STORE = 0,     // D = A B^T (+ bias)                      -> bf16 [M,N]
   EPI_LOGPROB = 1,   // fused lm-head log-prob partials          -> float4 [n_splits, M]
   EPI_DLOGITS = 2,   // dZ = (onehot - softmax) * g / T          -> bf16 [M,N]
+  EPI_SWIGLU = 4,    // D[M, N/2] = silu(gate) * up with [32 gate | 32 up] interleaved weight rows   -> bf16
   EPI_MERGE = 3,     // D = addend + scale * (A B^T)  (K-BC LoRA merge: W + (alpha/r) B A) -> bf16 [M,N]
 };
 

@@ -42,6 +42,31 @@ struct RowVec<__nv_bfloat16> {
   }
 };
 
+// Visit every element of a row: thread t owns vectors t, t+T, t+2T, ...; four independent 16-byte loads are
+// issued before any of them is consumed (memory-level parallelism: the passes are latency- not bandwidth-bound).
+template <typename T, typename F>
+NRL_DEVICE void for_each_elem(const T* z, int nvec, int V, F&& f) {
+  constexpr int VN = RowVec<T>::N;
+  constexpr int U = 4;
+  for (int v0 = threadIdx.x; v0 < nvec; v0 += U * kSampThreads) {
+    float x[U][VN];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int v = v0 + u * kSampThreads;
+      if (v < nvec) RowVec<T>::load(z, v, x[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int v = v0 + u * kSampThreads;
+      if (v < nvec) {
+#pragma unroll
+        for (int j = 0; j < VN; ++j)
+          if (v * VN + j < V) f(v * VN + j, x[u][j]);
+      }
+    }
+  }
+}
+
 NRL_DEVICE float block_reduce_sum(float v, float* red) {
   v = warp_sum(v);
   __syncthreads();
@@ -111,30 +136,18 @@ __global__ void __launch_bounds__(kSampThreads) sample_top_p_kernel(const T* __r
 
   // ---- pass 1: row maximum ----
   float mx = -INFINITY;
-  for (int v = tid; v < nvec; v += kSampThreads) {
-    float x[VN];
-    RowVec<T>::load(z, v, x);
-#pragma unroll
-    for (int j = 0; j < VN; ++j)
-      if (v * VN + j < V) mx = fmaxf(mx, x[j] * sc);
-  }
+  for_each_elem(z, nvec, V, [&](int, float x) { mx = fmaxf(mx, x * sc); });
   mx = block_reduce_max(mx, red);
 
   float thresh = INFINITY;                                // keep tokens with (mx - z) < thresh  [octaves below the max]
   if (top_p < 1.f) {
     // ---- pass 2: one-octave mass histogram ----
     hist_clear(s_hist);
-    for (int v = tid; v < nvec; v += kSampThreads) {
-      float x[VN];
-      RowVec<T>::load(z, v, x);
-#pragma unroll
-      for (int j = 0; j < VN; ++j)
-        if (v * VN + j < V) {
-          const float d = mx - x[j] * sc;
-          const int b = min(63, static_cast<int>(d));
-          my_hist[b * 32] += exp2f(-d);
-        }
-    }
+    for_each_elem(z, nvec, V, [&](int, float x) {
+      const float d = mx - x * sc;
+      const int b = min(63, static_cast<int>(d));
+      my_hist[b * 32] += exp2f(-d);
+    });
     hist_reduce(s_hist, s_acc);
     float total = 0.f;
     for (int k = 0; k < 64; ++k) total += s_acc[k];
@@ -148,20 +161,14 @@ __global__ void __launch_bounds__(kSampThreads) sample_top_p_kernel(const T* __r
     __syncthreads();
     // ---- pass 3: 1/64-octave histogram inside octave B ----
     hist_clear(s_hist);
-    for (int v = tid; v < nvec; v += kSampThreads) {
-      float x[VN];
-      RowVec<T>::load(z, v, x);
-#pragma unroll
-      for (int j = 0; j < VN; ++j)
-        if (v * VN + j < V) {
-          const float d = mx - x[j] * sc;
-          const int b = min(63, static_cast<int>(d));
-          if (b == B) {
-            const int f = min(63, static_cast<int>((d - static_cast<float>(B)) * 64.f));
-            my_hist[f * 32] += exp2f(-d);
-          }
-        }
-    }
+    for_each_elem(z, nvec, V, [&](int, float x) {
+      const float d = mx - x * sc;
+      const int b = min(63, static_cast<int>(d));
+      if (b == B) {
+        const int f = min(63, static_cast<int>((d - static_cast<float>(B)) * 64.f));
+        my_hist[f * 32] += exp2f(-d);
+      }
+    });
     hist_reduce(s_hist, s_acc);
     int Fc = 63;
     cum = before;
@@ -175,16 +182,10 @@ __global__ void __launch_bounds__(kSampThreads) sample_top_p_kernel(const T* __r
 
   // ---- pass 4: kept mass per thread (thread-major order), then draw and walk ----
   float mine = 0.f;
-  for (int v = tid; v < nvec; v += kSampThreads) {
-    float x[VN];
-    RowVec<T>::load(z, v, x);
-#pragma unroll
-    for (int j = 0; j < VN; ++j)
-      if (v * VN + j < V) {
-        const float d = mx - x[j] * sc;
-        if (d < thresh) mine += exp2f(-d);
-      }
-  }
+  for_each_elem(z, nvec, V, [&](int, float x) {
+    const float d = mx - x * sc;
+    if (d < thresh) mine += exp2f(-d);
+  });
   chunk_sum[tid] = mine;
   __syncthreads();
   if (tid < 32) {

@@ -42,6 +42,15 @@ def _bias(mod):
     return b
 
 
+def interleave_gate_up(lw, F: int):
+    """[gate | up] -> per 32 features [32 gate rows | 32 up rows]: the layout the fused SwiGLU GEMM epilogue
+    (EPI_SWIGLU) expects, so silu(gate)*up happens in registers and the [tokens, 2F] tensor never exists."""
+    if getattr(lw, "wgu_i", None) is None or F % 32 != 0:
+        return
+    d = lw.wgu.shape[1]
+    lw.wgu_i.view(F // 32, 2, 32, d).copy_(lw.wgu.view(2, F // 32, 32, d).transpose(0, 1))
+
+
 @torch.no_grad()
 def refresh_layer(sampler, li: int):
     cfg = sampler.cfg
@@ -60,6 +69,7 @@ def refresh_layer(sampler, li: int):
     _merged(at.o_proj, lw.wo)
     _merged(mlp.gate_proj, lw.wgu[:F])
     _merged(mlp.up_proj, lw.wgu[F:])
+    interleave_gate_up(lw, F)
     _merged(mlp.down_proj, lw.wdown)
     lw.ln1 = layer.input_layernorm.weight
     lw.ln2 = layer.post_attention_layernorm.weight
@@ -142,3 +152,5 @@ class ShardedWeightSync:
                     lw.bqkv[sl].copy_(b)
             lw.ln1, lw.ln2 = layer.input_layernorm.weight, layer.post_attention_layernorm.weight
         self.hdl.barrier(channel=1)                         # every peer's stores have landed
+        for lw in s.layers:
+            interleave_gate_up(lw, F)

@@ -30,7 +30,7 @@ def _unwrap(model):
 
 
 class _LayerWeights:
-    __slots__ = ("wqkv", "bqkv", "wo", "wgu", "wdown", "ln1", "ln2")
+    __slots__ = ("wqkv", "bqkv", "wo", "wgu", "wgu_i", "wdown", "ln1", "ln2")
 
 
 class NativeSampler:
@@ -77,6 +77,8 @@ class NativeSampler:
             lw.bqkv = torch.zeros(nq + 2 * nkv, dtype=torch.bfloat16, device=dev)
             lw.wo = torch.empty(d, nq, dtype=torch.bfloat16, device=dev)
             lw.wgu = torch.empty(2 * F, d, dtype=torch.bfloat16, device=dev)
+            # gate/up rows interleaved per 32 features for the fused SwiGLU GEMM epilogue
+            lw.wgu_i = torch.empty(2 * F, d, dtype=torch.bfloat16, device=dev) if (F % 64 == 0) else None
             lw.wdown = torch.empty(d, F, dtype=torch.bfloat16, device=dev)
             self.layers.append(lw)
 
@@ -138,8 +140,14 @@ class NativeSampler:
         att = attention_varlen(q, k, v, cu, max_len, causal=True)
         o = native.gemm_bf16(att.reshape(T, Hq * D), lw.wo)
         h, res = native.add_rmsnorm(o, res, lw.ln2, cfg.rms_norm_eps)
-        act = native.ext().swiglu(native.gemm_bf16(h, lw.wgu))
-        return native.gemm_bf16(act, lw.wdown), res
+        return native.gemm_bf16(self._mlp_act(lw, h), lw.wdown), res
+
+    def _mlp_act(self, lw, h):
+        if lw.wgu_i is not None:
+            native._count()
+            return native.ext().gemm_swiglu(h, lw.wgu_i, None)
+        native._count(2)
+        return native.ext().swiglu(native.gemm_bf16(h, lw.wgu))
 
     def _layer_decode(self, li, x, res, cos, sin, st):
         cfg, lw = self.cfg, self.layers[li]
@@ -160,9 +168,8 @@ class NativeSampler:
                                   1.0 / math.sqrt(D), st["splits"])
         o = native.gemm_bf16(att.view(S, Hq * D), lw.wo)
         h, res = native.add_rmsnorm(o, res, lw.ln2, cfg.rms_norm_eps)
-        act = native.ext().swiglu(native.gemm_bf16(h, lw.wgu))
-        native._count(3)
-        return native.gemm_bf16(act, lw.wdown), res
+        native._count(2)
+        return native.gemm_bf16(self._mlp_act(lw, h), lw.wdown), res
 
     def _final_logits(self, x, res):
         cfg = self.cfg

@@ -289,3 +289,18 @@ def test_lora_merge_kernel():
         arena = torch.zeros(N + 64, K, device="cuda", dtype=torch.bfloat16)
         n.ext().lora_merge(w, a, b, 0.25, arena[32:32 + N])
         assert torch.equal(arena[32:32 + N], out) and arena[:32].abs().sum() == 0 and arena[32 + N:].abs().sum() == 0
+
+
+def test_gemm_swiglu_fused():
+    n = _native()
+    torch.manual_seed(0)
+    for (M, F, K) in ((300, 512, 256), (2048, 8960, 1536), (77, 64, 128)):
+        x = torch.randn(M, K, device="cuda").bfloat16()
+        wg = (torch.randn(F, K, device="cuda") * 0.05).bfloat16()
+        wu = (torch.randn(F, K, device="cuda") * 0.05).bfloat16()
+        wi = torch.empty(2 * F, K, device="cuda", dtype=torch.bfloat16)
+        wi.view(F // 32, 2, 32, K).copy_(torch.stack([wg.view(F // 32, 32, K), wu.view(F // 32, 32, K)], 1))
+        out = n.ext().gemm_swiglu(x, wi, None)
+        g, u = x.float() @ wg.float().t(), x.float() @ wu.float().t()
+        want = torch.nn.functional.silu(g) * u
+        assert _rel(out, want) < 2e-2, (M, F, K)
