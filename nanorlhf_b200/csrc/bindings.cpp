@@ -92,6 +92,43 @@ torch::Tensor gemm_swiglu(const torch::Tensor& a, const torch::Tensor& w_interle
   return out;
 }
 
+// ---- fp8 rollout path ------------------------------------------------------------------------------------
+std::tuple<torch::Tensor, torch::Tensor> quant_rows_e4m3(const torch::Tensor& x) {
+  check_bf16_2d(x, "x");
+  c10::cuda::CUDAGuard guard(x.device());
+  const int64_t M = x.size(0), K = x.size(1);
+  TORCH_CHECK(K % 16 == 0, "K must be a multiple of 16");
+  torch::Tensor q = torch::empty({M, K}, x.options().dtype(torch::kUInt8));
+  torch::Tensor sc = torch::empty({M}, x.options().dtype(torch::kFloat32));
+  check(nrl_quant_rows_e4m3(x.data_ptr(), x.stride(0), q.data_ptr(), K, sc.data_ptr<float>(), M, K, cur_stream()), "quant_rows_e4m3");
+  return {q, sc};
+}
+
+// D[M,N] (bf16) = (Aq[M,K] Bq[N,K]^T) * a_scale[M] * b_scale[N] (+bias); swiglu=true: Bq rows interleaved, D[M,N/2]
+torch::Tensor gemm_fp8(const torch::Tensor& aq, const torch::Tensor& a_scale, const torch::Tensor& bq, const torch::Tensor& b_scale,
+                       const c10::optional<torch::Tensor>& bias, bool swiglu) {
+  TORCH_CHECK(aq.is_cuda() && aq.scalar_type() == torch::kUInt8 && aq.dim() == 2 && aq.stride(1) == 1 && aq.stride(0) % 16 == 0);
+  TORCH_CHECK(bq.is_cuda() && bq.scalar_type() == torch::kUInt8 && bq.dim() == 2 && bq.stride(1) == 1 && bq.stride(0) % 16 == 0);
+  const int64_t M = aq.size(0), K = aq.size(1), N = bq.size(0);
+  TORCH_CHECK(bq.size(1) == K && K % 16 == 0 && N % 8 == 0);
+  TORCH_CHECK(a_scale.scalar_type() == torch::kFloat32 && a_scale.numel() == M && b_scale.scalar_type() == torch::kFloat32 && b_scale.numel() == N);
+  c10::cuda::CUDAGuard guard(aq.device());
+  const int64_t No = swiglu ? N / 2 : N;
+  torch::Tensor out = torch::empty({M, No}, aq.options().dtype(torch::kBFloat16));
+  if (M == 0) return out;
+  const int bn = pick_block_n(M, N);
+  CUtensorMap tmA = nrl::make_tma_2d(aq.data_ptr(), M, K, aq.stride(0), 128, 128, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1);
+  CUtensorMap tmB = nrl::make_tma_2d(bq.data_ptr(), N, K, bq.stride(0), bn, 128, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1);
+  CUtensorMap tmD = nrl::make_tma_2d(out.data_ptr(), M, No, out.stride(0) * 2, 128, 64, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2);
+  nrl::GemmParams p{};
+  p.M = M; p.N = N; p.K = K; p.n_splits = 1; p.scale = 1.f;
+  p.row_scale = a_scale.data_ptr<float>();
+  p.col_scale = b_scale.data_ptr<float>();
+  if (bias.has_value()) p.bias = reinterpret_cast<const __nv_bfloat16*>(bias->data_ptr());
+  check(nrl_gemm_fp8_tn(&tmA, &tmB, &tmD, &p, bn, swiglu ? nrl::EPI_SWIGLU : nrl::EPI_STORE, num_sms(), cur_stream()), "gemm_fp8");
+  return out;
+}
+
 int pick_splits(int64_t M, int64_t N, int bn) {
   int64_t num_m = (M + 127) / 128, num_n = (N + bn - 1) / bn;
   int64_t s = (num_sms() + num_m - 1) / num_m;       // enough work items to cover the SMs
@@ -501,6 +538,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("inv_temperature"), py::arg("n_splits") = 0);
   m.def("lmhead_dlogits", &lmhead_dlogits);
   m.def("lora_merge", &lora_merge);
+  m.def("quant_rows_e4m3", &quant_rows_e4m3);
+  m.def("gemm_fp8", &gemm_fp8, py::arg("aq"), py::arg("a_scale"), py::arg("bq"), py::arg("b_scale"), py::arg("bias") = py::none(),
+        py::arg("swiglu") = false);
   m.def("gemm_swiglu", &gemm_swiglu, py::arg("a"), py::arg("w_interleaved"), py::arg("out") = py::none());
   m.def("rmsnorm", &rmsnorm, py::arg("x"), py::arg("w"), py::arg("eps"), py::arg("residual") = py::none(),
         py::arg("want_rstd") = false);

@@ -58,7 +58,10 @@ NRL_DEVICE TileCoord tile_coord(int t, int num_m, int num_n) {
   return c;
 }
 
-template <int BLOCK_N, int EPI>
+// FP8 = true: A and B are e4m3 bytes (one k-block = 128 elements = the same 128-byte swizzle row), the MMA is
+// tcgen05 kind::f8f6f4 (K = 32 per instruction, 2x the bf16 rate) and the epilogue applies the per-row (token)
+// and per-column (output channel) dequantisation scales.
+template <int BLOCK_N, int EPI, bool FP8 = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmD, GemmParams p) {
@@ -74,7 +77,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int lane = threadIdx.x & 31;
   const int num_m = (p.M + BLOCK_M - 1) / BLOCK_M;
   const int num_n_total = (p.N + BLOCK_N - 1) / BLOCK_N;
-  const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+  constexpr int kElemsPerKBlock = FP8 ? 128 : BLOCK_K;          // 128 bytes of K per stage either way
+  const int num_kb = (p.K + kElemsPerKBlock - 1) / kElemsPerKBlock;
   // EPI_LOGPROB: a work item is (m tile, vocab split) and walks n tiles [n_begin, n_end) itself
   const int n_splits = (EPI == EPI_LOGPROB) ? p.n_splits : 1;
   const int n_per_split = (EPI == EPI_LOGPROB) ? (num_n_total + n_splits - 1) / n_splits : 1;
@@ -130,8 +134,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             uint8_t* sa = smem + stage * L::kStageBytes;
             uint8_t* sb = sa + L::kABytes;
             mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
-            tma_load_2d(sa, &tmA, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
-            tma_load_2d(sb, &tmB, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N);
+            tma_load_2d(sa, &tmA, &full_bar[stage], kb * kElemsPerKBlock, m_blk * BLOCK_M);
+            tma_load_2d(sb, &tmB, &full_bar[stage], kb * kElemsPerKBlock, n_blk * BLOCK_N);
             if (++stage == L::kStages) { stage = 0; phase ^= 1; }
           }
         }
@@ -140,7 +144,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N, 1, 1);   // bf16 x bf16 -> fp32
+      constexpr uint32_t idesc = FP8 ? make_idesc(BLOCK_M, BLOCK_N, 0, 0)    // e4m3 x e4m3 -> fp32
+                                     : make_idesc(BLOCK_M, BLOCK_N, 1, 1);   // bf16 x bf16 -> fp32
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -165,7 +170,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
               uint64_t adesc = make_smem_desc_sw128(a_addr + k * UMMA_K * 2);
               uint64_t bdesc = make_smem_desc_sw128(b_addr + k * UMMA_K * 2);
-              umma_f16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+              if (FP8) umma_f8(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+              else umma_f16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
             }
             umma_commit(&empty_bar[stage]);          // smem stage reusable once these MMAs retire
             if (++stage == L::kStages) { stage = 0; phase ^= 1; }
@@ -269,10 +275,16 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             // ---- fused SwiGLU: the weight rows are interleaved so that every 64-column chunk of the tile is
             //      [32 gate | 32 up] of the same 32 features; two chunks make one 64-wide output slab ----
             uint32_t cur[16];
+            const float rs = (FP8 && row_ok) ? p.row_scale[row] : 1.f;
 #pragma unroll
             for (int j = 0; j < 32; j += 2) {
-              const float g0 = __uint_as_float(v[0][j]), g1 = __uint_as_float(v[0][j + 1]);
-              const float u0 = __uint_as_float(v[1][j]), u1 = __uint_as_float(v[1][j + 1]);
+              float g0 = __uint_as_float(v[0][j]), g1 = __uint_as_float(v[0][j + 1]);
+              float u0 = __uint_as_float(v[1][j]), u1 = __uint_as_float(v[1][j + 1]);
+              if (FP8) {
+                const int cg = min(col0 + j, p.N - 2), cu = min(col0 + 32 + j, p.N - 2);
+                g0 *= rs * p.col_scale[cg]; g1 *= rs * p.col_scale[cg + 1];
+                u0 *= rs * p.col_scale[cu]; u1 *= rs * p.col_scale[cu + 1];
+              }
               cur[j / 2] = pack_bf16x2(g0 / (1.f + exp2f(-g0 * kLog2e)) * u0, g1 / (1.f + exp2f(-g1 * kLog2e)) * u1);
             }
             if ((c & 1) == 0) {
@@ -323,6 +335,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     x0 += __bfloat162float(p.addend[static_cast<long>(row) * p.addend_stride + col]);
                   }
                 } else if (EPI == EPI_STORE) {
+                  if (FP8) {
+                    const float rs = row_ok ? p.row_scale[row] : 0.f;
+                    x0 *= rs * ((col < p.N) ? p.col_scale[col] : 0.f);
+                    x1 *= rs * ((col + 1 < p.N) ? p.col_scale[col + 1] : 0.f);
+                  }
                   if (p.bias != nullptr) {
                     if (col < p.N) x0 += __bfloat162float(p.bias[col]);
                     if (col + 1 < p.N) x1 += __bfloat162float(p.bias[col + 1]);
@@ -397,11 +414,11 @@ __global__ void lmhead_combine_kernel(const float4* __restrict__ partials, int M
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-template <int BLOCK_N, int EPI>
+template <int BLOCK_N, int EPI, bool FP8 = false>
 static cudaError_t launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD,
                                const GemmParams& p, int num_sms, cudaStream_t stream) {
   using L = SmemLayout<BLOCK_N>;
-  auto kern = gemm_bf16_tn_kernel<BLOCK_N, EPI>;
+  auto kern = gemm_bf16_tn_kernel<BLOCK_N, EPI, FP8>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
@@ -435,6 +452,20 @@ extern "C" cudaError_t nrl_gemm_bf16_tn(const CUtensorMap* tmA, const CUtensorMa
     if (epi == EPI_STORE) return launch_impl<128, EPI_STORE>(*tmA, *tmB, *tmD, *p, num_sms, stream);
     if (epi == EPI_LOGPROB) return launch_impl<128, EPI_LOGPROB>(*tmA, *tmB, *tmD, *p, num_sms, stream);
     if (epi == EPI_DLOGITS) return launch_impl<128, EPI_DLOGITS>(*tmA, *tmB, *tmD, *p, num_sms, stream);
+  }
+  return cudaErrorInvalidValue;
+}
+
+extern "C" cudaError_t nrl_gemm_fp8_tn(const CUtensorMap* tmA, const CUtensorMap* tmB, const CUtensorMap* tmD,
+                                       const nrl::GemmParams* p, int block_n, int epi, int num_sms, cudaStream_t stream) {
+  using namespace nrl;
+  if (p->row_scale == nullptr || p->col_scale == nullptr) return cudaErrorInvalidValue;
+  if (block_n == 256) {
+    if (epi == EPI_STORE) return launch_impl<256, EPI_STORE, true>(*tmA, *tmB, *tmD, *p, num_sms, stream);
+    if (epi == EPI_SWIGLU) return launch_impl<256, EPI_SWIGLU, true>(*tmA, *tmB, *tmD, *p, num_sms, stream);
+  } else if (block_n == 128) {
+    if (epi == EPI_STORE) return launch_impl<128, EPI_STORE, true>(*tmA, *tmB, *tmD, *p, num_sms, stream);
+    if (epi == EPI_SWIGLU) return launch_impl<128, EPI_SWIGLU, true>(*tmA, *tmB, *tmD, *p, num_sms, stream);
   }
   return cudaErrorInvalidValue;
 }

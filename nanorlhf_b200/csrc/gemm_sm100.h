@@ -23,6 +23,8 @@ struct GemmParams {
   const float* lse;             // EPI_DLOGITS: [M]
   const float* grad_logp;       // EPI_DLOGITS: [M]
   float* partials;              // EPI_LOGPROB: [n_splits, M, 4]
+  const float* row_scale;       // fp8 GEMM: [M] per-token dequant scale of A
+  const float* col_scale;       // fp8 GEMM: [N] per-output-channel dequant scale of B
   const __nv_bfloat16* addend;  // EPI_MERGE: [M, N] row-major, row stride addend_stride elements
   long addend_stride;
 };
@@ -32,5 +34,7 @@ struct GemmParams {
 extern "C" cudaError_t nrl_gemm_bf16_tn(const CUtensorMap* tmA, const CUtensorMap* tmB, const CUtensorMap* tmD,
                                         const nrl::GemmParams* p, int block_n, int epi, int num_sms,
                                         cudaStream_t stream);
+extern "C" cudaError_t nrl_gemm_fp8_tn(const CUtensorMap* tmA, const CUtensorMap* tmB, const CUtensorMap* tmD,
+                                       const nrl::GemmParams* p, int block_n, int epi, int num_sms, cudaStream_t stream);
 extern "C" cudaError_t nrl_lmhead_combine(const float* partials, int M, int n_splits, float* logp, float* entropy,
                                           float* lse, cudaStream_t stream);

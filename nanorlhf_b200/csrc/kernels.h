@@ -66,3 +66,6 @@ cudaError_t nrl_attn_varlen_bwd(const void* dout, const void* q, const void* k, 
                                 long os, const int* cu, int num_seqs, int total, int Hq, int Hkv, int D, float scale,
                                 cudaStream_t s);
 }
+
+extern "C" cudaError_t nrl_quant_rows_e4m3(const void* x, long x_stride, void* q, long q_stride, float* scale, int M, int K,
+                                           cudaStream_t s);

@@ -30,7 +30,7 @@ def _unwrap(model):
 
 
 class _LayerWeights:
-    __slots__ = ("wqkv", "bqkv", "wo", "wgu", "wgu_i", "wdown", "ln1", "ln2")
+    __slots__ = ("wqkv", "bqkv", "wo", "wgu", "wgu_i", "wdown", "ln1", "ln2", "q8")
 
 
 class NativeSampler:
@@ -80,7 +80,25 @@ class NativeSampler:
             # gate/up rows interleaved per 32 features for the fused SwiGLU GEMM epilogue
             lw.wgu_i = torch.empty(2 * F, d, dtype=torch.bfloat16, device=dev) if (F % 64 == 0) else None
             lw.wdown = torch.empty(d, F, dtype=torch.bfloat16, device=dev)
+            lw.q8 = None          # fp8 rollout: {name: (e4m3 weight, per-channel scale)} built at weight refresh
             self.layers.append(lw)
+
+    # ---- linear layers of the sampler: bf16 tcgen05 GEMM, or e4m3 x e4m3 (per-token x per-channel scales) ----
+    def _lin(self, lw, name, x, bias=None):
+        if lw.q8 is not None:
+            native._count(2)
+            xq, xs = native.ext().quant_rows_e4m3(x)
+            wq, ws = lw.q8[name]
+            return native.ext().gemm_fp8(xq, xs, wq, ws, bias, False)
+        return native.gemm_bf16(x, getattr(lw, name), bias)
+
+    def quantize_arena(self):
+        """fp8 rollout (rollout_dtype="fp8"): e4m3 copies of the merged arena with per-output-channel scales."""
+        for lw in self.layers:
+            lw.q8 = {}
+            for name in ("wqkv", "wo", "wdown") + (("wgu_i",) if lw.wgu_i is not None else ("wgu",)):
+                native._count()
+                lw.q8[name] = native.ext().quant_rows_e4m3(getattr(lw, name))
 
     def weights_fingerprint(self):
         """Cheap change detector: the optimizer bumps ``_nrl_version`` on the policy after every step."""
@@ -94,6 +112,8 @@ class NativeSampler:
         if not force and self._weights_version == ver:
             return
         refresh_sampler_arena(self)
+        if self.rollout_dtype == "fp8":
+            self.quantize_arena()
         self._weights_version = ver
 
     # ------------------------------------------------------------------------------------------
@@ -129,7 +149,7 @@ class NativeSampler:
         cfg, lw = self.cfg, self.layers[li]
         D, Hq, Hkv = cfg.head_dim, cfg.num_attention_heads, cfg.num_key_value_heads
         h, res = (native.rmsnorm(x, lw.ln1, cfg.rms_norm_eps), x) if res is None else native.add_rmsnorm(x, res, lw.ln1, cfg.rms_norm_eps)
-        qkv = native.gemm_bf16(h, lw.wqkv, lw.bqkv)
+        qkv = self._lin(lw, "wqkv", h, lw.bqkv)
         T = qkv.shape[0]
         q = qkv[:, :Hq * D].view(T, Hq, D)
         k = qkv[:, Hq * D:(Hq + Hkv) * D].view(T, Hkv, D)
@@ -138,11 +158,19 @@ class NativeSampler:
         native.ext().rope(k, cos, sin, 1.0, True)
         native.kv_cache_write(k, v, self.k_cache[li], self.v_cache[li], slot, src)
         att = attention_varlen(q, k, v, cu, max_len, causal=True)
-        o = native.gemm_bf16(att.reshape(T, Hq * D), lw.wo)
+        o = self._lin(lw, "wo", att.reshape(T, Hq * D))
         h, res = native.add_rmsnorm(o, res, lw.ln2, cfg.rms_norm_eps)
-        return native.gemm_bf16(self._mlp_act(lw, h), lw.wdown), res
+        return self._lin(lw, "wdown", self._mlp_act(lw, h)), res
 
     def _mlp_act(self, lw, h):
+        if lw.q8 is not None:
+            native._count(2)
+            hq, hs = native.ext().quant_rows_e4m3(h)
+            if lw.wgu_i is not None:
+                wq, ws = lw.q8["wgu_i"]
+                return native.ext().gemm_fp8(hq, hs, wq, ws, None, True)
+            wq, ws = lw.q8["wgu"]
+            return native.ext().swiglu(native.ext().gemm_fp8(hq, hs, wq, ws, None, False))
         if lw.wgu_i is not None:
             native._count()
             return native.ext().gemm_swiglu(h, lw.wgu_i, None)
@@ -156,7 +184,7 @@ class NativeSampler:
             h, res = native.ext().rmsnorm(x, lw.ln1, cfg.rms_norm_eps, None, False)[0], x
         else:
             h, res = native.add_rmsnorm(x, res, lw.ln1, cfg.rms_norm_eps)
-        qkv = native.gemm_bf16(h, lw.wqkv, lw.bqkv)
+        qkv = self._lin(lw, "wqkv", h, lw.bqkv)
         S = qkv.shape[0]
         q = qkv[:, :Hq * D].view(S, Hq, D)
         k = qkv[:, Hq * D:(Hq + Hkv) * D].view(S, Hkv, D)
@@ -166,10 +194,10 @@ class NativeSampler:
         native.kv_cache_write(k, v, self.k_cache[li], self.v_cache[li], st["slot"])
         att = native.paged_decode(q, self.k_cache[li], self.v_cache[li], st["block_tables"], st["ctx_lens"],
                                   1.0 / math.sqrt(D), st["splits"])
-        o = native.gemm_bf16(att.view(S, Hq * D), lw.wo)
+        o = self._lin(lw, "wo", att.view(S, Hq * D))
         h, res = native.add_rmsnorm(o, res, lw.ln2, cfg.rms_norm_eps)
         native._count(2)
-        return native.gemm_bf16(self._mlp_act(lw, h), lw.wdown), res
+        return self._lin(lw, "wdown", self._mlp_act(lw, h)), res
 
     def _final_logits(self, x, res):
         cfg = self.cfg
