@@ -528,6 +528,48 @@ void allreduce_sum(const std::vector<int64_t>& buf_ptrs, int64_t lo, int64_t n, 
                           static_cast<int>(max_blocks), cur_stream()), "allreduce_sum");
 }
 
+void kv_cache_write_fp8(const torch::Tensor& k, const torch::Tensor& v, torch::Tensor kq, torch::Tensor vq, torch::Tensor ks,
+                        torch::Tensor vs, const torch::Tensor& slot_mapping, const c10::optional<torch::Tensor>& src_index) {
+  TORCH_CHECK(k.dim() == 3 && v.dim() == 3 && k.stride(2) == 1 && k.stride(1) == k.size(2) && v.stride(2) == 1 && v.stride(1) == v.size(2));
+  TORCH_CHECK(kq.scalar_type() == torch::kUInt8 && kq.dim() == 4 && kq.is_contiguous() && vq.is_contiguous());
+  TORCH_CHECK(ks.scalar_type() == torch::kFloat32 && ks.is_contiguous() && vs.is_contiguous());
+  TORCH_CHECK(slot_mapping.scalar_type() == torch::kInt32 && slot_mapping.is_contiguous());
+  const int* src = nullptr;
+  if (src_index.has_value()) {
+    TORCH_CHECK(src_index->scalar_type() == torch::kInt32 && src_index->numel() == slot_mapping.numel());
+    src = src_index->data_ptr<int>();
+  } else {
+    TORCH_CHECK(slot_mapping.numel() == k.size(0));
+  }
+  c10::cuda::CUDAGuard guard(k.device());
+  check(nrl_kv_cache_write_fp8(k.data_ptr(), v.data_ptr(), k.stride(0), v.stride(0), kq.data_ptr(), vq.data_ptr(), ks.data_ptr<float>(),
+                               vs.data_ptr<float>(), slot_mapping.data_ptr<int>(), src, slot_mapping.numel(), k.size(1), k.size(2),
+                               kq.size(2), cur_stream()), "kv_cache_write_fp8");
+}
+
+torch::Tensor paged_decode_fp8(const torch::Tensor& q, const torch::Tensor& kq, const torch::Tensor& vq, const torch::Tensor& ks,
+                               const torch::Tensor& vs, const torch::Tensor& block_tables, const torch::Tensor& context_lens,
+                               double scale, int64_t splits) {
+  TORCH_CHECK(q.is_cuda() && q.scalar_type() == torch::kBFloat16 && q.dim() == 3 && q.stride(2) == 1 && q.stride(1) == q.size(2));
+  TORCH_CHECK(block_tables.scalar_type() == torch::kInt32 && block_tables.is_contiguous() && context_lens.scalar_type() == torch::kInt32);
+  c10::cuda::CUDAGuard guard(q.device());
+  const int S = q.size(0), Hq = q.size(1), D = q.size(2), Hkv = kq.size(1);
+  torch::Tensor out = torch::empty({S, Hq, D}, q.options());
+  torch::Tensor po, pml;
+  float *pop = nullptr, *pmlp = nullptr;
+  if (splits > 1) {
+    po = torch::empty({S, Hkv, splits, 8, D}, q.options().dtype(torch::kFloat32));
+    pml = torch::empty({S, Hkv, splits, 8, 2}, q.options().dtype(torch::kFloat32));
+    pop = po.data_ptr<float>();
+    pmlp = pml.data_ptr<float>();
+  }
+  check(nrl_paged_decode_fp8(q.data_ptr(), q.stride(0), kq.data_ptr(), vq.data_ptr(), ks.data_ptr<float>(), vs.data_ptr<float>(),
+                             block_tables.data_ptr<int>(), context_lens.data_ptr<int>(), out.data_ptr(), pop, pmlp, S, Hq, Hkv, D,
+                             kq.size(2), block_tables.size(1), static_cast<int>(splits), static_cast<float>(scale), cur_stream()),
+        "paged_decode_fp8");
+  return out;
+}
+
 }  // namespace
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
@@ -564,6 +606,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("scale"), py::arg("causal") = true, py::arg("rel_a") = py::none(), py::arg("rel_b") = py::none(),
         py::arg("lut") = py::none());
   m.def("attn_varlen_bwd", &attn_varlen_bwd);
+  m.def("kv_cache_write_fp8", &kv_cache_write_fp8, py::arg("k"), py::arg("v"), py::arg("kq"), py::arg("vq"), py::arg("ks"), py::arg("vs"),
+        py::arg("slot_mapping"), py::arg("src_index") = py::none());
+  m.def("paged_decode_fp8", &paged_decode_fp8);
   m.def("allreduce_adam", &allreduce_adam);
   m.def("allreduce_sum", &allreduce_sum);
   nrl::bind_runtime(m);

@@ -69,3 +69,12 @@ cudaError_t nrl_attn_varlen_bwd(const void* dout, const void* q, const void* k, 
 
 extern "C" cudaError_t nrl_quant_rows_e4m3(const void* x, long x_stride, void* q, long q_stride, float* scale, int M, int K,
                                            cudaStream_t s);
+
+extern "C" {
+cudaError_t nrl_kv_cache_write_fp8(const void* k, const void* v, long k_stride_t, long v_stride_t, void* kq, void* vq, float* ks,
+                                   float* vs, const int* slot_mapping, const int* src_index, int pairs, int Hkv, int head_dim,
+                                   int page, cudaStream_t s);
+cudaError_t nrl_paged_decode_fp8(const void* q, long q_stride_s, const void* kq, const void* vq, const float* ks, const float* vs,
+                                 const int* block_tables, const int* context_lens, void* out, float* part_o, float* part_ml, int S,
+                                 int Hq, int Hkv, int head_dim, int page, int max_blocks, int splits, float scale, cudaStream_t s);
+}

@@ -123,7 +123,7 @@ class NativeSampler:
         cfg = self.cfg
         if self.num_blocks >= blocks_needed:
             return
-        per_block = 2 * cfg.num_hidden_layers * cfg.num_key_value_heads * self.PAGE * cfg.head_dim * 2
+        per_block = 2 * cfg.num_hidden_layers * cfg.num_key_value_heads * self.PAGE * cfg.head_dim * (1 if self.rollout_dtype == "fp8" else 2)
         self.k_cache, self.v_cache = [], []
         self._graphs.clear()
         torch.cuda.empty_cache() if self.num_blocks else None
@@ -134,9 +134,14 @@ class NativeSampler:
         if n < 64:
             raise RuntimeError("not enough free HBM for a KV cache")
         shape = (n, cfg.num_key_value_heads, self.PAGE, cfg.head_dim)
+        kv_dtype = torch.uint8 if self.rollout_dtype == "fp8" else torch.bfloat16
+        self.k_scale, self.v_scale = [], []
         for _ in range(cfg.num_hidden_layers):
-            self.k_cache.append(torch.zeros(shape, dtype=torch.bfloat16, device=self.device))
-            self.v_cache.append(torch.zeros(shape, dtype=torch.bfloat16, device=self.device))
+            self.k_cache.append(torch.zeros(shape, dtype=kv_dtype, device=self.device))
+            self.v_cache.append(torch.zeros(shape, dtype=kv_dtype, device=self.device))
+            if self.rollout_dtype == "fp8":     # e4m3 pages + one fp32 scale per (token, kv head)
+                self.k_scale.append(torch.ones(shape[:3], dtype=torch.float32, device=self.device))
+                self.v_scale.append(torch.ones(shape[:3], dtype=torch.float32, device=self.device))
         self.num_blocks = n
 
     # ------------------------------------------------------------------------------------------
@@ -156,11 +161,18 @@ class NativeSampler:
         v = qkv[:, (Hq + Hkv) * D:].view(T, Hkv, D)
         native.ext().rope(q, cos, sin, 1.0, True)
         native.ext().rope(k, cos, sin, 1.0, True)
-        native.kv_cache_write(k, v, self.k_cache[li], self.v_cache[li], slot, src)
+        self._kv_write(li, k, v, slot, src)
         att = attention_varlen(q, k, v, cu, max_len, causal=True)
         o = self._lin(lw, "wo", att.reshape(T, Hq * D))
         h, res = native.add_rmsnorm(o, res, lw.ln2, cfg.rms_norm_eps)
         return self._lin(lw, "wdown", self._mlp_act(lw, h)), res
+
+    def _kv_write(self, li, k, v, slot, src):
+        if self.rollout_dtype == "fp8":
+            native._count()
+            native.ext().kv_cache_write_fp8(k, v, self.k_cache[li], self.v_cache[li], self.k_scale[li], self.v_scale[li], slot, src)
+        else:
+            native.kv_cache_write(k, v, self.k_cache[li], self.v_cache[li], slot, src)
 
     def _mlp_act(self, lw, h):
         if lw.q8 is not None:
@@ -191,9 +203,14 @@ class NativeSampler:
         v = qkv[:, (Hq + Hkv) * D:].view(S, Hkv, D)
         native.ext().rope(q, cos, sin, 1.0, True)
         native.ext().rope(k, cos, sin, 1.0, True)
-        native.kv_cache_write(k, v, self.k_cache[li], self.v_cache[li], st["slot"])
-        att = native.paged_decode(q, self.k_cache[li], self.v_cache[li], st["block_tables"], st["ctx_lens"],
-                                  1.0 / math.sqrt(D), st["splits"])
+        self._kv_write(li, k, v, st["slot"], None)
+        if self.rollout_dtype == "fp8":
+            native._count()
+            att = native.ext().paged_decode_fp8(q, self.k_cache[li], self.v_cache[li], self.k_scale[li], self.v_scale[li],
+                                                st["block_tables"], st["ctx_lens"], 1.0 / math.sqrt(D), st["splits"])
+        else:
+            att = native.paged_decode(q, self.k_cache[li], self.v_cache[li], st["block_tables"], st["ctx_lens"],
+                                      1.0 / math.sqrt(D), st["splits"])
         o = self._lin(lw, "wo", att.view(S, Hq * D))
         h, res = native.add_rmsnorm(o, res, lw.ln2, cfg.rms_norm_eps)
         native._count(2)

@@ -343,3 +343,31 @@ def test_sampler_fp8_rollout_close_to_bf16():
     ob = b.generate(prompts, 1, 0.0, 1.0, 16, None, 2047, 1)
     assert ob.shape == oa.shape and (ob != 2047).all()
     assert (oa[:, 0] == ob[:, 0]).float().mean().item() >= 0.75      # greedy first tokens mostly agree under fp8 noise
+
+
+@pytest.mark.parametrize("Hq,Hkv,splits", [(12, 2, 1), (28, 4, 2)])
+def test_paged_decode_fp8_kv(Hq, Hkv, splits):
+    n = _native()
+    torch.manual_seed(0)
+    S, D, bs, nblk = 21, 128, 16, 400
+    ctx = torch.randint(1, 200, (S,), device="cuda", dtype=torch.int32)
+    ctx[0], ctx[1] = 1, 16
+    maxb = int((ctx.max().item() + bs - 1) // bs)
+    table = torch.randperm(nblk, device="cuda")[: S * maxb].view(S, maxb).to(torch.int32)
+    kq = torch.zeros(nblk, Hkv, bs, D, device="cuda", dtype=torch.uint8)
+    vq = torch.zeros_like(kq)
+    ks = torch.ones(nblk, Hkv, bs, device="cuda")
+    vs = torch.ones_like(ks)
+    # fill every slot through the fp8 page writer
+    T = nblk * bs
+    k = torch.randn(T, Hkv, D, device="cuda").bfloat16() * 2
+    v = torch.randn(T, Hkv, D, device="cuda").bfloat16()
+    slots = torch.arange(T, device="cuda", dtype=torch.int32)
+    n.ext().kv_cache_write_fp8(k, v, kq, vq, ks, vs, slots, None)
+    kd = (kq.view(torch.float8_e4m3fn).float() * ks[..., None]).bfloat16()
+    vd = (vq.view(torch.float8_e4m3fn).float() * vs[..., None]).bfloat16()
+    assert _rel(kd.permute(0, 2, 1, 3).reshape(T, Hkv, D), k) < 0.05
+    q = torch.randn(S, Hq, D, device="cuda").bfloat16()
+    out = n.ext().paged_decode_fp8(q, kq, vq, ks, vs, table, ctx, 1.0 / math.sqrt(D), splits)
+    want = ref.paged_attention_decode(q, kd, vd, table, ctx)      # oracle on the dequantised cache
+    assert _rel(out, want) < 2e-2
