@@ -54,3 +54,26 @@ def test_sampling_is_seeded_and_eos_stops():
         if eos in row:
             i = row.index(eos)
             assert all(t == 2047 for t in row[i + 1:])
+
+
+def test_waves_under_kv_pressure_match_unconstrained():
+    """Continuous batching: with a KV pool that holds only a fraction of the requests the scheduler admits them in
+    waves (pages of finished sequences are recycled); greedy outputs must equal the all-at-once run."""
+    from nanorlhf_b200.sampler.native_sampler import NativeSampler
+    m = _models()
+    g = torch.Generator().manual_seed(1)
+    prompts = [torch.randint(0, 2000, (int(L),), generator=g).tolist() for L in torch.randint(4, 60, (12,), generator=g)]
+    big = NativeSampler(m, kv_cache_gb=1.0, sync_every=8)
+    big.sync_weights()
+    ref_out = big.generate(prompts, 2, 0.0, 1.0, 40, None, 2047, 1)
+    # an "eos" that actually occurs, so sequences finish at different steps
+    eos = int(ref_out[:, 5:30].flatten().mode().values)
+    want = big.generate(prompts, 2, 0.0, 1.0, 40, eos, 2047, 1)
+    small = NativeSampler(m, kv_cache_gb=0.0032, sync_every=4)      # ~65 pages: a third of what all 24 sequences need
+    small.sync_weights()
+    got = small.generate(prompts, 2, 0.0, 1.0, 40, eos, 2047, 1)
+    assert small.num_blocks < 100
+    assert torch.equal(got, want)
+    capped = NativeSampler(m, kv_cache_gb=1.0, sync_every=4, max_num_seqs=6)
+    capped.sync_weights()
+    assert torch.equal(capped.generate(prompts, 2, 0.0, 1.0, 40, eos, 2047, 1), want)
