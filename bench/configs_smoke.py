@@ -80,7 +80,7 @@ if "r1" in which:
     tok = tok_for(shape)
     policy = get_peft_model(Qwen2ForCausalLM.from_config(shape, torch.bfloat16, dev, seed=0), LoraConfig(r=64, lora_alpha=16, modules_to_save=None))
     ref = Qwen2ForCausalLM.from_config(shape, torch.bfloat16, dev, seed=0)
-    cfg = base_cfg("r1", kl_coef=0.0, response_length=512, rollout_dtype="fp8", total_episodes=32)
+    cfg = base_cfg("r1", kl_coef=0.0, response_length=512, rollout_dtype="fp8", kv_cache_dtype="fp8", total_episodes=32)
     cfg.grpo_sample_N = 4
     ds = synthetic_token_dataset(128, shape.vocab_size - 2, 24, 96, seed=1)
 

@@ -62,7 +62,8 @@ class RLConfig:
     stop_token_id: Optional[int] = None
     missing_eos_penalty: Optional[float] = None
     changing_seed: bool = True                  # seed=random.randint(1,5000) per rollout (:127)
-    rollout_dtype: str = "bf16"                 # bf16 | fp8 (block-scaled e4m3 weights + fp8 KV)
+    rollout_dtype: str = "bf16"                 # sampler GEMMs: bf16 | fp8 (e4m3, per-token x per-channel scales)
+    kv_cache_dtype: str = "bf16"                # sampler KV pages: bf16 | fp8 (e4m3 + per-token scales; 2x capacity)
     sampler: str = "auto"                       # auto | native | torch
     kv_block_size: int = 16
 

@@ -38,7 +38,7 @@ class NativeSampler:
 
     def __init__(self, model, rollout_dtype: str = "bf16", kv_block_size: int = 16, max_num_seqs: int = 4096,
                  kv_memory_fraction: float = 0.85, prefill_token_budget: int = 32768, sync_every: int = 64,
-                 use_cuda_graph: bool = True, kv_cache_gb: Optional[float] = None):
+                 use_cuda_graph: bool = True, kv_cache_gb: Optional[float] = None, kv_cache_dtype: Optional[str] = None):
         if kv_block_size != self.PAGE:
             raise ValueError("the decode attention kernel is built for 16-token pages")
         native.load()
@@ -48,7 +48,10 @@ class NativeSampler:
         self.device = next(self.lm.parameters()).device
         if self.cfg.head_dim != 128:
             raise ValueError("native sampler kernels are specialised for head_dim 128 (Qwen2.5 family)")
-        self.rollout_dtype = rollout_dtype
+        self.rollout_dtype = rollout_dtype              # GEMM operands: bf16 | fp8 (e4m3, per-token x per-channel scales)
+        # KV pages: bf16 | fp8.  fp8 pages halve KV memory (2x the resident sequences); the fp8 decode kernel is
+        # not faster than the bf16 one yet (in-smem dequant makes it issue-bound), so bf16 stays the default.
+        self.kv_dtype = kv_cache_dtype or "bf16"
         self.max_num_seqs = max_num_seqs
         self.kv_memory_fraction = kv_memory_fraction
         self.kv_cache_gb = kv_cache_gb
@@ -123,7 +126,7 @@ class NativeSampler:
         cfg = self.cfg
         if self.num_blocks >= blocks_needed:
             return
-        per_block = 2 * cfg.num_hidden_layers * cfg.num_key_value_heads * self.PAGE * cfg.head_dim * (1 if self.rollout_dtype == "fp8" else 2)
+        per_block = 2 * cfg.num_hidden_layers * cfg.num_key_value_heads * self.PAGE * cfg.head_dim * (1 if self.kv_dtype == "fp8" else 2)
         self.k_cache, self.v_cache = [], []
         self._graphs.clear()
         torch.cuda.empty_cache() if self.num_blocks else None
@@ -134,12 +137,12 @@ class NativeSampler:
         if n < 64:
             raise RuntimeError("not enough free HBM for a KV cache")
         shape = (n, cfg.num_key_value_heads, self.PAGE, cfg.head_dim)
-        kv_dtype = torch.uint8 if self.rollout_dtype == "fp8" else torch.bfloat16
+        kv_dtype = torch.uint8 if self.kv_dtype == "fp8" else torch.bfloat16
         self.k_scale, self.v_scale = [], []
         for _ in range(cfg.num_hidden_layers):
             self.k_cache.append(torch.zeros(shape, dtype=kv_dtype, device=self.device))
             self.v_cache.append(torch.zeros(shape, dtype=kv_dtype, device=self.device))
-            if self.rollout_dtype == "fp8":     # e4m3 pages + one fp32 scale per (token, kv head)
+            if self.kv_dtype == "fp8":     # e4m3 pages + one fp32 scale per (token, kv head)
                 self.k_scale.append(torch.ones(shape[:3], dtype=torch.float32, device=self.device))
                 self.v_scale.append(torch.ones(shape[:3], dtype=torch.float32, device=self.device))
         self.num_blocks = n
@@ -168,7 +171,7 @@ class NativeSampler:
         return self._lin(lw, "wdown", self._mlp_act(lw, h)), res
 
     def _kv_write(self, li, k, v, slot, src):
-        if self.rollout_dtype == "fp8":
+        if self.kv_dtype == "fp8":
             native._count()
             native.ext().kv_cache_write_fp8(k, v, self.k_cache[li], self.v_cache[li], self.k_scale[li], self.v_scale[li], slot, src)
         else:
@@ -204,7 +207,7 @@ class NativeSampler:
         native.ext().rope(q, cos, sin, 1.0, True)
         native.ext().rope(k, cos, sin, 1.0, True)
         self._kv_write(li, k, v, st["slot"], None)
-        if self.rollout_dtype == "fp8":
+        if self.kv_dtype == "fp8":
             native._count()
             att = native.ext().paged_decode_fp8(q, self.k_cache[li], self.v_cache[li], self.k_scale[li], self.v_scale[li],
                                                 st["block_tables"], st["ctx_lens"], 1.0 / math.sqrt(D), st["splits"])

@@ -190,7 +190,8 @@ class RemaxTrainer(RLTrainer):
         # second, greedy (T=0) pass on the same resident engine -- no re-boot (remax_trainer.py:166-179)
         out["baseline_responses"] = sampler_engine.generate(
             1, self.model, self.tokenizer, queries, 0.0, a.response_length, top_p=1.0, seed=0,
-            backend=a.sampler, rollout_dtype=a.rollout_dtype, kv_block_size=a.kv_block_size)
+            backend=a.sampler, rollout_dtype=a.rollout_dtype, kv_block_size=a.kv_block_size,
+                                            kv_cache_dtype=a.kv_cache_dtype)
         return out
 
     def post_score(self, queries, rollout, scores):

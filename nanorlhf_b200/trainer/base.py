@@ -184,7 +184,8 @@ class RLTrainer:
         responses = sampler_engine.generate(self.samples_per_prompt, self.model, self.tokenizer, queries,
                                             a.temperature, a.response_length, top_p=a.top_p,
                                             seed=seed + self.comm.rank * 7919, backend=a.sampler,
-                                            rollout_dtype=a.rollout_dtype, kv_block_size=a.kv_block_size)
+                                            rollout_dtype=a.rollout_dtype, kv_block_size=a.kv_block_size,
+                                            kv_cache_dtype=a.kv_cache_dtype)
         return {"responses": responses}
 
     def score(self, queries: torch.Tensor, responses: torch.Tensor) -> torch.Tensor:

@@ -337,7 +337,7 @@ def test_sampler_fp8_rollout_close_to_bf16():
     prompts = [torch.randint(0, 2000, (int(L),), generator=g).tolist() for L in (5, 16, 17, 33)]
     a = NativeSampler(m, kv_cache_gb=1.0, sync_every=8)
     a.sync_weights()
-    b = NativeSampler(m, rollout_dtype="fp8", kv_cache_gb=1.0, sync_every=8)
+    b = NativeSampler(m, rollout_dtype="fp8", kv_cache_dtype="fp8", kv_cache_gb=1.0, sync_every=8)
     b.sync_weights()
     oa = a.generate(prompts, 1, 0.0, 1.0, 16, None, 2047, 1)
     ob = b.generate(prompts, 1, 0.0, 1.0, 16, None, 2047, 1)
