@@ -1,0 +1,343 @@
+// tcgen05 / TMEM / TMA flash-attention FORWARD (causal, packed varlen, GQA, head_dim 128) for sm_100a.
+//
+// One CTA = 128 query rows of one head; KV is streamed in blocks of 128 keys.
+//   warp 0       TMA producer : Q tile once, then K_j / V_j tiles (2-stage ring), 128B-swizzled panels of 64 dims
+//   warp 1       MMA issuer   : S_j = Q K_j^T   (8 x tcgen05.mma 128x128x16, both operands K-major)  -> TMEM S[j%2]
+//                               O  += P_j V_j   (8 x tcgen05.mma 128x128x16, A = P in smem K-major, B = V MN-major)
+//   warps 2..5   softmax      : thread i owns query row i (TMEM lane i): tcgen05.ld S -> scale/mask -> online max ->
+//                               exp2 -> bf16 P into swizzled smem; rescales O in TMEM when the row max moves;
+//                               final O / l and LSE written straight to global memory
+// S is double buffered in TMEM so QK^T of block j+1 overlaps the softmax of block j; P is double buffered in smem.
+// TMEM: S0 [0,128) S1 [128,256) O [256,384).  SMEM: Q 32 KB + 2 x (K 32 KB + V 32 KB) + 2 x P 32 KB = 224 KB.
+// The mma.sync kernels in attention_varlen.cu remain the backward path and the oracle for this kernel.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace nrl {
+
+constexpr int kTcD = 128;                 // head dim
+constexpr int kTcBM = 128;                // query rows per CTA
+constexpr int kTcBN = 128;                // keys per block
+constexpr int kPanel = 128 * 128;         // bytes of one [128 rows][64 x bf16] swizzled panel (16 KB)
+constexpr int kTile = 2 * kPanel;         // [128][128] bf16 = two panels (32 KB)
+constexpr int kTcThreads = 192;
+
+struct AttnTcParams {
+  const int* cu_seqlens;
+  __nv_bfloat16* out;
+  float* lse;                 // [Hq, T_total]
+  long o_stride_t;
+  int num_seqs, total_tokens, Hq, G;
+  float scale_log2;
+};
+
+struct AttnTcSmem {
+  static constexpr int kQ = 0;
+  static constexpr int kK = kTile;                       // 2 stages
+  static constexpr int kV = kK + 2 * kTile;              // 2 stages
+  static constexpr int kP = kV + 2 * kTile;              // 2 buffers
+  static constexpr int kBar = kP + 2 * kTile;
+  static constexpr int kTotal = kBar + 256;
+};
+
+// MN-major (N contiguous) 128B-swizzled operand: panels of 64 elements along N are `lbo_bytes` apart, groups of 8
+// K-rows (128 B each) are 1024 B apart.
+NRL_DEVICE uint64_t make_smem_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+NRL_DEVICE constexpr uint32_t make_idesc_bmn(uint32_t M, uint32_t N) {      // bf16, fp32 accum, A K-major, B MN-major
+  return (1u << 4) | (1u << 7) | (1u << 10) | (0u << 15) | (1u << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+NRL_DEVICE void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+NRL_DEVICE void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ bool tc_locate_block(const int* cu, int num_seqs, int blk, int& m_blk, int& seq_start, int& seq_len) {
+  __shared__ int s_info[4];
+  if (threadIdx.x == 0) {
+    int acc = 0, found = 0;
+    for (int s = 0; s < num_seqs; ++s) {
+      const int a = cu[s], b = cu[s + 1];
+      const int nb = (b - a + kTcBM - 1) / kTcBM;
+      if (blk < acc + nb) {
+        s_info[0] = 1; s_info[1] = blk - acc; s_info[2] = a; s_info[3] = b - a;
+        found = 1;
+        break;
+      }
+      acc += nb;
+    }
+    if (!found) s_info[0] = 0;
+  }
+  __syncthreads();
+  if (!s_info[0]) return false;
+  m_blk = s_info[1]; seq_start = s_info[2]; seq_len = s_info[3];
+  return true;
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, AttnTcParams p) {
+  using L = AttnTcSmem;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* q_full = reinterpret_cast<uint64_t*>(smem + L::kBar);
+  uint64_t* kv_full = q_full + 1;       // [2]
+  uint64_t* kv_empty = kv_full + 2;     // [2]
+  uint64_t* s_full = kv_empty + 2;      // [2]
+  uint64_t* p_ready = s_full + 2;       // [2]
+  uint64_t* o_done = p_ready + 2;       // [1]  PV of a block retired (O readable / rescalable, P[buf] reusable)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_done + 1);
+
+  int m_blk, seq_start, seq_len;
+  // heaviest (latest) query blocks are launched first: longest-processing-time order trims the causal tail
+  if (!tc_locate_block(p.cu_seqlens, p.num_seqs, gridDim.x - 1 - blockIdx.x, m_blk, seq_start, seq_len)) return;
+  const int head = blockIdx.y, kvh = head / p.G;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = m_blk * kTcBM;
+  const int n_blocks = min((seq_len + kTcBN - 1) / kTcBN, (q0 + kTcBM + kTcBN - 1) / kTcBN);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_ready[i], 4);        // one arrive per softmax warp
+    }
+    mbar_init(o_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    __syncwarp();
+    tmem_alloc(tmem_ptr, 512);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t t_o = tmem_base + 256;
+
+  if (warp == 0) {
+    // ============================== TMA producer ==============================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, kTile);
+      tma_load_2d(smem + L::kQ, &tmQ, q_full, head * kTcD, seq_start + q0);
+      tma_load_2d(smem + L::kQ + kPanel, &tmQ, q_full, head * kTcD + 64, seq_start + q0);
+      uint32_t phase = 0;
+      for (int j = 0; j < n_blocks; ++j) {
+        const int st = j & 1;
+        mbar_wait(&kv_empty[st], phase ^ 1);
+        uint8_t* sk = smem + L::kK + st * kTile;
+        uint8_t* sv = smem + L::kV + st * kTile;
+        mbar_arrive_expect_tx(&kv_full[st], 2 * kTile);
+        const int row = seq_start + j * kTcBN;
+        tma_load_2d(sk, &tmK, &kv_full[st], kvh * kTcD, row);
+        tma_load_2d(sk + kPanel, &tmK, &kv_full[st], kvh * kTcD + 64, row);
+        tma_load_2d(sv, &tmV, &kv_full[st], kvh * kTcD, row);
+        tma_load_2d(sv + kPanel, &tmV, &kv_full[st], kvh * kTcD + 64, row);
+        if (st == 1) phase ^= 1;
+      }
+    }
+  } else if (warp == 1) {
+    // ============================== MMA issuer ==============================
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc(kTcBM, kTcBN, 1, 1);       // Q K^T : both K-major
+      constexpr uint32_t idesc_o = make_idesc_bmn(kTcBM, kTcD);         // P V   : B = V is MN-major
+      const uint32_t q_addr = smem_u32(smem + L::kQ);
+      mbar_wait(q_full, 0);
+      tc_fence_after();
+      auto issue_s = [&](int j) {
+        const int st = j & 1;
+        mbar_wait(&kv_full[st], (j >> 1) & 1);
+        tc_fence_after();
+        const uint32_t k_addr = smem_u32(smem + L::kK + st * kTile);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {          // 8 x 16 dims; dims 0-63 in panel 0, 64-127 in panel 1
+          const uint32_t off = (k >> 2) * kPanel + (k & 3) * 32;
+          umma_f16(tmem_base + st * kTcBN, make_smem_desc_sw128(q_addr + off), make_smem_desc_sw128(k_addr + off), idesc_s,
+                   k != 0 ? 1u : 0u);
+        }
+        umma_commit(&s_full[st]);
+      };
+      issue_s(0);
+      for (int j = 0; j < n_blocks; ++j) {
+        const int st = j & 1;
+        if (j + 1 < n_blocks) issue_s(j + 1);               // overlaps the softmax of block j
+        mbar_wait(&p_ready[st], (j >> 1) & 1);              // P_j in smem, O rescaled
+        tc_fence_after();
+        const uint32_t p_addr = smem_u32(smem + L::kP + st * kTile);
+        const uint32_t v_addr = smem_u32(smem + L::kV + st * kTile);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {          // 8 x 16 keys; keys 0-63 in P panel 0, 64-127 in panel 1
+          const uint64_t adesc = make_smem_desc_sw128(p_addr + (k >> 2) * kPanel + (k & 3) * 32);
+          const uint64_t bdesc = make_smem_desc_sw128_mn(v_addr + k * 16 * 128, kPanel);
+          umma_f16(t_o, adesc, bdesc, idesc_o, (j | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&kv_empty[st]);            // K_j / V_j smem reusable
+        umma_commit(o_done);                   // O and P[st] consistent again
+      }
+    }
+    __syncwarp();
+  } else {
+    // ============================== softmax / correction / epilogue ==============================
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;                          // row in tile == TMEM lane
+    const int row = q0 + r;
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    float m_run = -INFINITY, l_run = 0.f;
+    for (int j = 0; j < n_blocks; ++j) {
+      const int st = j & 1;
+      mbar_wait(&s_full[st], (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t t_s = tmem_base + st * kTcBN + lane_off;
+      uint32_t sv[4][32];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x32(t_s + c * 32, sv[c]);
+      tmem_ld_wait();
+      const int key0 = j * kTcBN;
+      // only the diagonal block and a ragged last block need masking (CTA-uniform test)
+      if (key0 + kTcBN - 1 > q0 || key0 + kTcBN > seq_len) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int key = key0 + c * 32 + i;
+            if (key >= seq_len || key > row) sv[c][i] = 0xff800000u;      // -inf
+          }
+      }
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};         // 4 independent chains
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(sv[c][i]));
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * p.scale_log2;
+      // lazy rescale: keep the stale maximum while the new one is < 2^8 above it (p <= 256 is exact enough in bf16
+      // and l / O stay consistent with m_run); key 0 is live for every row so m_new is finite from block 0 on
+      const float m_new = (mx - m_run > 8.f) ? mx : m_run;
+      const float corr = exp2f(m_run - m_new);
+      float ps4[4] = {0.f, 0.f, 0.f, 0.f};
+      // exponentials (in place: sv[c][i/2] <- bf16x2(p_i, p_i+1)); the wait below overlaps them
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float p0 = exp2f(fmaf(__uint_as_float(sv[c][i]), p.scale_log2, -m_new));
+          const float p1 = exp2f(fmaf(__uint_as_float(sv[c][i + 1]), p.scale_log2, -m_new));
+          ps4[(i >> 1) & 3] += p0 + p1;
+          sv[c][i / 2] = pack_bf16x2(p0, p1);
+        }
+      const float ps = (ps4[0] + ps4[1]) + (ps4[2] + ps4[3]);
+      // PV of block j-1 must have retired before O is rescaled; it also implies PV(j-2) is done with P[st].
+      // o_done completes once per block: block j-1's completion has parity (j-1)&1.
+      if (j > 0) {
+        mbar_wait(o_done, (j - 1) & 1);
+        tc_fence_after();
+      }
+      uint8_t* pbuf = smem + L::kP + st * kTile;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        // keys c*32 .. c*32+31 of row r: panel c/2, 16-byte chunks (c&1)*4 .. +3 of the 128-byte row
+        uint8_t* rowp = pbuf + (c >> 1) * kPanel + r * 128;
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const int ch = (c & 1) * 4 + q4;
+          *reinterpret_cast<uint4*>(rowp + ((ch ^ (r & 7)) << 4)) =
+              make_uint4(sv[c][q4 * 4], sv[c][q4 * 4 + 1], sv[c][q4 * 4 + 2], sv[c][q4 * 4 + 3]);
+        }
+      }
+      l_run = l_run * corr + ps;
+      // ---- rescale O in TMEM when this row's maximum moved (skipped warp-wide when nobody needs it) ----
+      const bool need = (j > 0) && (corr != 1.f);
+      if (__any_sync(0xffffffffu, need)) {
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t ov[32];
+          tmem_ld_32x32b_x32(t_o + lane_off + c * 32, ov);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * corr);
+          tmem_st_32x32b_x32(t_o + lane_off + c * 32, ov);
+        }
+        tmem_st_wait();
+      }
+      m_run = m_new;
+      fence_proxy_async_smem();              // P writes visible to the tensor-core (async) proxy
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_ready[st]);
+    }
+    // ---- epilogue: O / l -> bf16, LSE ----
+    mbar_wait(o_done, (n_blocks - 1) & 1);
+    tc_fence_after();
+    const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+    const bool row_ok = row < seq_len;
+    __nv_bfloat16* orow = p.out + static_cast<long>(seq_start + row) * p.o_stride_t + head * kTcD;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t ov[32];
+      tmem_ld_32x32b_x32(t_o + lane_off + c * 32, ov);
+      tmem_ld_wait();
+      if (row_ok) {
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          uint4 o4;
+          o4.x = pack_bf16x2(__uint_as_float(ov[q4 * 8]) * inv, __uint_as_float(ov[q4 * 8 + 1]) * inv);
+          o4.y = pack_bf16x2(__uint_as_float(ov[q4 * 8 + 2]) * inv, __uint_as_float(ov[q4 * 8 + 3]) * inv);
+          o4.z = pack_bf16x2(__uint_as_float(ov[q4 * 8 + 4]) * inv, __uint_as_float(ov[q4 * 8 + 5]) * inv);
+          o4.w = pack_bf16x2(__uint_as_float(ov[q4 * 8 + 6]) * inv, __uint_as_float(ov[q4 * 8 + 7]) * inv);
+          *reinterpret_cast<uint4*>(orow + c * 32 + q4 * 8) = o4;
+        }
+      }
+    }
+    if (row_ok && p.lse != nullptr)
+      p.lse[static_cast<long>(head) * p.total_tokens + seq_start + row] = (m_run + log2f(l_run)) * 0.6931471805599453f;
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace nrl
+
+extern "C" cudaError_t nrl_attn_fwd_tc(const CUtensorMap* tmQ, const CUtensorMap* tmK, const CUtensorMap* tmV, void* out,
+                                       float* lse, long o_stride_t, const int* cu, int num_seqs, int total, int Hq, int Hkv,
+                                       float scale, cudaStream_t s) {
+  using namespace nrl;
+  if (total == 0) return cudaSuccess;
+  AttnTcParams p;
+  p.cu_seqlens = cu; p.out = static_cast<__nv_bfloat16*>(out); p.lse = lse; p.o_stride_t = o_stride_t;
+  p.num_seqs = num_seqs; p.total_tokens = total; p.Hq = Hq; p.G = Hq / Hkv;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnTcSmem::kTotal);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  dim3 grid(total / kTcBM + num_seqs, Hq);
+  attn_fwd_tc_kernel<<<grid, kTcThreads, AttnTcSmem::kTotal, s>>>(*tmQ, *tmK, *tmV, p);
+  return cudaGetLastError();
+}

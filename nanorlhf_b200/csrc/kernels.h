@@ -1,5 +1,6 @@
 // C launch API of the non-GEMM kernels (elementwise.cu, rl_kernels.cu, sampling.cu, attention.cu, comm.cu).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -65,6 +66,10 @@ cudaError_t nrl_attn_varlen_bwd(const void* dout, const void* q, const void* k, 
                                 const float* lse, float* delta, void* dq, void* dk, void* dv, long qs, long ks, long vs,
                                 long os, const int* cu, int num_seqs, int total, int Hq, int Hkv, int D, float scale,
                                 cudaStream_t s);
+// tcgen05 forward (attention_fwd_tc.cu): causal, head_dim 128, q/k/v addressed through TMA maps over [T, H*D]
+cudaError_t nrl_attn_fwd_tc(const CUtensorMap* tmQ, const CUtensorMap* tmK, const CUtensorMap* tmV, void* out, float* lse,
+                            long o_stride_t, const int* cu, int num_seqs, int total, int Hq, int Hkv, float scale,
+                            cudaStream_t s);
 }
 
 extern "C" cudaError_t nrl_quant_rows_e4m3(const void* x, long x_stride, void* q, long q_stride, float* scale, int M, int K,

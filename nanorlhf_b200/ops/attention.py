@@ -1,8 +1,9 @@
 """Packed-varlen causal GQA attention on CUDA (training / log-prob / prefill path).
 
-Native kernels: ``csrc/attention_varlen.cu`` (forward + backward, mma.sync tensor-core flash
-attention).  Until those are validated on hardware the op can run on the flash-attn library
-(``NANORLHF_ATTN=flash_attn``); that path is the *baseline* this framework replaces
+Native kernels: forward = ``csrc/attention_fwd_tc.cu`` (tcgen05 MMAs with TMEM accumulators, TMA-fed,
+warp-specialised; head_dim 128), backward (and the forward for other head sizes / ``NANORLHF_ATTN_TC=0``)
+= ``csrc/attention_varlen.cu`` (mma.sync flash attention).  ``NANORLHF_ATTN=flash_attn`` runs the flash-attn
+library instead; that path is the *baseline* this framework replaces
 (reference: attn_implementation="flash_attention_2", /root/reference/GRPO/grpo.py:219).
 """
 from __future__ import annotations
@@ -13,6 +14,7 @@ import os
 import torch
 
 _IMPL = os.environ.get("NANORLHF_ATTN", "auto")
+_USE_TC = os.environ.get("NANORLHF_ATTN_TC", "1") != "0"
 
 
 def _native_available() -> bool:
@@ -25,7 +27,10 @@ class _NativeAttn(torch.autograd.Function):
     def forward(ctx, q, k, v, cu_seqlens, max_seqlen, scale):
         from . import native
         native._count()
-        o, lse = native.ext().attn_varlen_fwd(q, k, v, cu_seqlens, int(max_seqlen), float(scale))
+        if _USE_TC and q.shape[-1] == 128:
+            o, lse = native.ext().attn_fwd_tc(q, k, v, cu_seqlens, float(scale))
+        else:
+            o, lse = native.ext().attn_varlen_fwd(q, k, v, cu_seqlens, int(max_seqlen), float(scale))
         ctx.save_for_backward(q, k, v, o, lse, cu_seqlens)
         ctx.max_seqlen, ctx.scale = int(max_seqlen), float(scale)
         return o

@@ -249,6 +249,26 @@ def test_attention_varlen_fwd_bwd(Hq, Hkv, D):
     assert _rel(q.grad, qr.grad) < 3e-2 and _rel(k.grad, kr.grad) < 3e-2 and _rel(v.grad, vr.grad) < 3e-2
 
 
+@pytest.mark.parametrize("Hq,Hkv,lens", [(4, 2, [1, 17, 128, 129, 200, 333]), (12, 2, [700, 1300, 64]), (2, 2, [2500])])
+def test_attention_fwd_tcgen05(Hq, Hkv, lens):
+    """tcgen05/TMEM forward (attention_fwd_tc.cu) vs the fp32 oracle, incl. lse and strided qkv views."""
+    n = _native()
+    torch.manual_seed(1)
+    D = 128
+    cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32, device="cuda")
+    T = sum(lens)
+    qkv = torch.randn(T, (Hq + 2 * Hkv) * D, device="cuda").bfloat16()
+    q = qkv[:, :Hq * D].view(T, Hq, D)
+    k = qkv[:, Hq * D:(Hq + Hkv) * D].view(T, Hkv, D)
+    v = qkv[:, (Hq + Hkv) * D:].view(T, Hkv, D)
+    o, lse = n.ext().attn_fwd_tc(q, k, v, cu, 1.0 / math.sqrt(D))
+    o2, lse2 = n.ext().attn_varlen_fwd(q, k, v, cu, max(lens), 1.0 / math.sqrt(D))
+    orf = ref.attention_varlen(q.float(), k.float(), v.float(), cu.cpu(), causal=True)
+    assert torch.isfinite(o.float()).all()
+    assert _rel(o, orf) < 2e-2, _rel(o, orf)
+    assert (lse - lse2).abs().max().item() < 2e-2
+
+
 def test_deberta_fused_attention_matches_eager():
     import os
     from nanorlhf_b200.models.deberta_v3 import DebertaV3Config, DebertaV3ForSequenceClassification
