@@ -41,4 +41,13 @@ if which in ("all", "attn"):
     v = torch.randn(T, 2, 128, device=dev, dtype=torch.bfloat16)
     for _ in range(2):
         native.ext().attn_varlen_fwd(q, k, v, cu, 1650, 1 / math.sqrt(128), True)
+if which in ("all", "attn_tc"):
+    lens = [4096] * 4
+    cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), device=dev, dtype=torch.int32)
+    T = sum(lens)
+    q = torch.randn(T, 12, 128, device=dev, dtype=torch.bfloat16)
+    k = torch.randn(T, 2, 128, device=dev, dtype=torch.bfloat16)
+    v = torch.randn(T, 2, 128, device=dev, dtype=torch.bfloat16)
+    for _ in range(2):
+        native.ext().attn_fwd_tc(q, k, v, cu, 1 / math.sqrt(128))
 torch.cuda.synchronize()
