@@ -471,7 +471,8 @@ std::tuple<torch::Tensor, torch::Tensor> attn_varlen_fwd(const torch::Tensor& q,
 
 // tcgen05 forward: causal, D = 128, bf16.  q/k/v may be strided views (row stride multiple of 8 elements).
 std::tuple<torch::Tensor, torch::Tensor> attn_fwd_tc(const torch::Tensor& q, const torch::Tensor& k, const torch::Tensor& v,
-                                                     const torch::Tensor& cu_seqlens, double scale) {
+                                                     const torch::Tensor& cu_seqlens, double scale,
+                                                     const c10::optional<torch::Tensor>& prof) {
   check_thd(q, "q"); check_thd(k, "k"); check_thd(v, "v");
   TORCH_CHECK(cu_seqlens.scalar_type() == torch::kInt32 && cu_seqlens.is_contiguous());
   c10::cuda::CUDAGuard guard(q.device());
@@ -479,13 +480,15 @@ std::tuple<torch::Tensor, torch::Tensor> attn_fwd_tc(const torch::Tensor& q, con
   TORCH_CHECK(D == 128 && Hq % Hkv == 0, "attn_fwd_tc: head_dim 128 only");
   torch::Tensor out = torch::empty({T, Hq, D}, q.options());
   torch::Tensor lse = torch::empty({Hq, T}, q.options().dtype(torch::kFloat32));
-  auto map_of = [&](const torch::Tensor& t, int H) {
-    return nrl::make_tma_2d(t.data_ptr(), T, static_cast<uint64_t>(H) * D, t.stride(0) * 2, 128, 64,
+  auto map_of = [&](const torch::Tensor& t, int H, int box_rows) {
+    return nrl::make_tma_2d(t.data_ptr(), T, static_cast<uint64_t>(H) * D, t.stride(0) * 2, box_rows, 64,
                             CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2);
   };
-  const CUtensorMap mq = map_of(q, Hq), mk = map_of(k, Hkv), mv = map_of(v, Hkv);
+  // Q tiles are 128 rows, K/V blocks 64 rows (attention_fwd_tc.cu)
+  const CUtensorMap mq = map_of(q, Hq, 128), mk = map_of(k, Hkv, 64), mv = map_of(v, Hkv, 64);
   check(nrl_attn_fwd_tc(&mq, &mk, &mv, out.data_ptr(), lse.data_ptr<float>(), out.stride(0), cu_seqlens.data_ptr<int>(),
-                        cu_seqlens.numel() - 1, T, Hq, Hkv, static_cast<float>(scale), cur_stream()), "attn_fwd_tc");
+                        cu_seqlens.numel() - 1, T, Hq, Hkv, static_cast<float>(scale), cur_stream(),
+                        prof.has_value() ? reinterpret_cast<long long*>(prof->data_ptr<int64_t>()) : nullptr), "attn_fwd_tc");
   return {out, lse};
 }
 
@@ -626,7 +629,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("scale"), py::arg("causal") = true, py::arg("rel_a") = py::none(), py::arg("rel_b") = py::none(),
         py::arg("lut") = py::none());
   m.def("attn_varlen_bwd", &attn_varlen_bwd);
-  m.def("attn_fwd_tc", &attn_fwd_tc);
+  m.def("attn_fwd_tc", &attn_fwd_tc, py::arg("q"), py::arg("k"), py::arg("v"), py::arg("cu_seqlens"), py::arg("scale"),
+        py::arg("prof") = py::none());
   m.def("kv_cache_write_fp8", &kv_cache_write_fp8, py::arg("k"), py::arg("v"), py::arg("kq"), py::arg("vq"), py::arg("ks"), py::arg("vs"),
         py::arg("slot_mapping"), py::arg("src_index") = py::none());
   m.def("paged_decode_fp8", &paged_decode_fp8);

@@ -26,6 +26,8 @@ CU_SOURCES = ["gemm_sm100.cu", "elementwise.cu", "rl_kernels.cu", "sampling.cu",
 CPP_SOURCES = ["bindings.cpp", "runtime.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--use_fast_math",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+if os.environ.get("NRL_ATTN_PROFILE") == "1":       # cycle accounting build of attention_fwd_tc.cu (bench/attn_prof.py)
+    NVCC_FLAGS.append("-DNRL_ATTN_PROFILE")
 
 
 def _stamp(path: str, extra: str) -> str:

@@ -112,7 +112,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   if (warp == 0) {
     // ===================================== TMA producer ======================================
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
@@ -143,7 +143,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================
-    if (lane == 0) {
+    // elect.sync instead of `lane == 0`: the compiler can then prove single-thread execution and emits the
+    // UTCHMMAs back to back instead of wrapping each one in an ELECT/branch loop (~13 instructions per MMA)
+    if (elect_one()) {
       constexpr uint32_t idesc = FP8 ? make_idesc(BLOCK_M, BLOCK_N, 0, 0)    // e4m3 x e4m3 -> fp32
                                      : make_idesc(BLOCK_M, BLOCK_N, 1, 1);   // bf16 x bf16 -> fp32
       int stage = 0;

@@ -69,7 +69,7 @@ cudaError_t nrl_attn_varlen_bwd(const void* dout, const void* q, const void* k, 
 // tcgen05 forward (attention_fwd_tc.cu): causal, head_dim 128, q/k/v addressed through TMA maps over [T, H*D]
 cudaError_t nrl_attn_fwd_tc(const CUtensorMap* tmQ, const CUtensorMap* tmK, const CUtensorMap* tmV, void* out, float* lse,
                             long o_stride_t, const int* cu, int num_seqs, int total, int Hq, int Hkv, float scale,
-                            cudaStream_t s);
+                            cudaStream_t s, long long* prof = nullptr);
 }
 
 extern "C" cudaError_t nrl_quant_rows_e4m3(const void* x, long x_stride, void* q, long q_stride, float* scale, int M, int K,
