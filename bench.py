@@ -224,6 +224,7 @@ def main():
         print(json.dumps(line), flush=True)
     trainer.heartbeat.close()
     comm.barrier()
+    comm.close()
     return 0
 
 

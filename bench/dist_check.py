@@ -44,6 +44,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--numel", type=int, default=540_672_000)      # ~LoRA r64 + embed + lm_head of Qwen2.5-1.5B
     ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--out", default=None, help="ignored (the result goes to gpurun_out/dist_check_<N>.json)")
     args = ap.parse_args()
     comm = Comm.from_env()
     dev, W, R = comm.device, comm.world_size, comm.rank
