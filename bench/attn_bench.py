@@ -38,11 +38,18 @@ def main():
         row = {"lens": f"{len(lens)}x{lens[0]}", "gflop": flops / 1e9}
         t = timeit(lambda: ext.attn_fwd_tc(q, k, v, cu, sc))
         row["tcgen05_ms"], row["tcgen05_tflops"] = t, flops / t / 1e9
+        o, lse = ext.attn_fwd_tc(q, k, v, cu, sc)
+        g = torch.randn_like(o)
+        bflops = 2.5 * flops
+        t = timeit(lambda: ext.attn_bwd_tc(g, q, k, v, o, lse, cu, sc))
+        row["bwd_tcgen05_ms"], row["bwd_tcgen05_tflops"] = t, bflops / t / 1e9
         if __import__("os").environ.get("ATTN_ONLY") == "tc":
             print(json.dumps(row), flush=True)
             continue
         t = timeit(lambda: ext.attn_varlen_fwd(q, k, v, cu, max(lens), sc))
         row["mma_sync_ms"], row["mma_sync_tflops"] = t, flops / t / 1e9
+        t = timeit(lambda: ext.attn_varlen_bwd(g, q, k, v, o, lse, cu, max(lens), sc))
+        row["bwd_mma_sync_ms"], row["bwd_mma_sync_tflops"] = t, bflops / t / 1e9
         try:
             from flash_attn import flash_attn_varlen_func
             t = timeit(lambda: flash_attn_varlen_func(q, k, v, cu, cu, max(lens), max(lens), softmax_scale=sc, causal=True))

@@ -514,6 +514,32 @@ std::tuple<torch::Tensor, torch::Tensor, torch::Tensor> attn_varlen_bwd(const to
   return {dq, dk, dv};
 }
 
+// tcgen05 backward: causal, D = 128, bf16, contiguous q/k/v/o/dout.
+std::tuple<torch::Tensor, torch::Tensor, torch::Tensor> attn_bwd_tc(const torch::Tensor& dout, const torch::Tensor& q,
+                                                                   const torch::Tensor& k, const torch::Tensor& v,
+                                                                   const torch::Tensor& o, const torch::Tensor& lse,
+                                                                   const torch::Tensor& cu_seqlens, double scale) {
+  check_thd(q, "q"); check_thd(k, "k"); check_thd(v, "v"); check_thd(o, "o"); check_thd(dout, "dout");
+  TORCH_CHECK(o.is_contiguous() && dout.is_contiguous() && dout.sizes() == o.sizes());
+  TORCH_CHECK(lse.scalar_type() == torch::kFloat32 && lse.is_contiguous());
+  c10::cuda::CUDAGuard guard(q.device());
+  const int T = q.size(0), Hq = q.size(1), D = q.size(2), Hkv = k.size(1);
+  TORCH_CHECK(D == 128 && Hq % Hkv == 0, "attn_bwd_tc: head_dim 128 only");
+  torch::Tensor dq = torch::empty({T, Hq, D}, q.options()), dk = torch::empty({T, Hkv, D}, q.options()),
+                dv = torch::empty({T, Hkv, D}, q.options());
+  torch::Tensor delta = torch::empty({Hq, T}, q.options().dtype(torch::kFloat32));
+  auto map_of = [&](const torch::Tensor& t, int H, int box_rows) {
+    return nrl::make_tma_2d(t.data_ptr(), T, static_cast<uint64_t>(H) * D, t.stride(0) * 2, box_rows, 64,
+                            CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2);
+  };
+  const CUtensorMap maps[8] = {map_of(q, Hq, 64),  map_of(dout, Hq, 64),  map_of(k, Hkv, 128), map_of(v, Hkv, 128),
+                               map_of(q, Hq, 128), map_of(dout, Hq, 128), map_of(k, Hkv, 64),  map_of(v, Hkv, 64)};
+  check(nrl_attn_bwd_tc(maps, o.data_ptr(), dout.data_ptr(), lse.data_ptr<float>(), delta.data_ptr<float>(), dq.data_ptr(),
+                        dk.data_ptr(), dv.data_ptr(), o.stride(0), dq.stride(0), dk.stride(0), cu_seqlens.data_ptr<int>(),
+                        cu_seqlens.numel() - 1, T, Hq, Hkv, static_cast<float>(scale), cur_stream()), "attn_bwd_tc");
+  return {dq, dk, dv};
+}
+
 // ---- K-AR: fused all-reduce + AdamW over symmetric memory ---------------------------------------------
 nrl::AdamHyper make_hyper(double lr, double beta1, double beta2, double eps, double wd, int64_t step, double grad_scale) {
   nrl::AdamHyper h;
@@ -629,6 +655,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("scale"), py::arg("causal") = true, py::arg("rel_a") = py::none(), py::arg("rel_b") = py::none(),
         py::arg("lut") = py::none());
   m.def("attn_varlen_bwd", &attn_varlen_bwd);
+  m.def("attn_bwd_tc", &attn_bwd_tc);
   m.def("attn_fwd_tc", &attn_fwd_tc, py::arg("q"), py::arg("k"), py::arg("v"), py::arg("cu_seqlens"), py::arg("scale"),
         py::arg("prof") = py::none());
   m.def("kv_cache_write_fp8", &kv_cache_write_fp8, py::arg("k"), py::arg("v"), py::arg("kq"), py::arg("vq"), py::arg("ks"), py::arg("vs"),

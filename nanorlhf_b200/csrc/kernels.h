@@ -70,6 +70,10 @@ cudaError_t nrl_attn_varlen_bwd(const void* dout, const void* q, const void* k, 
 cudaError_t nrl_attn_fwd_tc(const CUtensorMap* tmQ, const CUtensorMap* tmK, const CUtensorMap* tmV, void* out, float* lse,
                             long o_stride_t, const int* cu, int num_seqs, int total, int Hq, int Hkv, float scale,
                             cudaStream_t s, long long* prof = nullptr);
+// tcgen05 backward (attention_bwd_tc.cu): delta + dK/dV + dQ; `maps` = 8 tensor maps (see the .cu)
+cudaError_t nrl_attn_bwd_tc(const CUtensorMap* maps, const void* o, const void* dout, const float* lse, float* delta,
+                            void* dq, void* dk, void* dv, long o_stride_t, long dq_stride_t, long dkv_stride_t,
+                            const int* cu, int num_seqs, int total, int Hq, int Hkv, float scale, cudaStream_t s);
 }
 
 extern "C" cudaError_t nrl_quant_rows_e4m3(const void* x, long x_stride, void* q, long q_stride, float* scale, int M, int K,

@@ -1,8 +1,8 @@
 """Packed-varlen causal GQA attention on CUDA (training / log-prob / prefill path).
 
-Native kernels: forward = ``csrc/attention_fwd_tc.cu`` (tcgen05 MMAs with TMEM accumulators, TMA-fed,
-warp-specialised; head_dim 128), backward (and the forward for other head sizes / ``NANORLHF_ATTN_TC=0``)
-= ``csrc/attention_varlen.cu`` (mma.sync flash attention).  ``NANORLHF_ATTN=flash_attn`` runs the flash-attn
+Native kernels: ``csrc/attention_fwd_tc.cu`` / ``csrc/attention_bwd_tc.cu`` (tcgen05 MMAs with TMEM accumulators,
+TMA-fed, warp-specialised; head_dim 128); other head sizes and ``NANORLHF_ATTN_TC=0`` use
+``csrc/attention_varlen.cu`` (mma.sync flash attention, also the oracle of the tcgen05 kernels).  ``NANORLHF_ATTN=flash_attn`` runs the flash-attn
 library instead; that path is the *baseline* this framework replaces
 (reference: attn_implementation="flash_attention_2", /root/reference/GRPO/grpo.py:219).
 """
@@ -40,7 +40,10 @@ class _NativeAttn(torch.autograd.Function):
         from . import native
         q, k, v, o, lse, cu = ctx.saved_tensors
         native._count(3)
-        dq, dk, dv = native.ext().attn_varlen_bwd(do.contiguous(), q, k, v, o, lse, cu, ctx.max_seqlen, ctx.scale)
+        if _USE_TC and q.shape[-1] == 128 and q.is_contiguous() and k.is_contiguous() and v.is_contiguous():
+            dq, dk, dv = native.ext().attn_bwd_tc(do.contiguous(), q, k, v, o, lse, cu, ctx.scale)
+        else:
+            dq, dk, dv = native.ext().attn_varlen_bwd(do.contiguous(), q, k, v, o, lse, cu, ctx.max_seqlen, ctx.scale)
         return dq, dk, dv, None, None, None
 
 

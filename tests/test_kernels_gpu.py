@@ -269,6 +269,28 @@ def test_attention_fwd_tcgen05(Hq, Hkv, lens):
     assert (lse - lse2).abs().max().item() < 2e-2
 
 
+@pytest.mark.parametrize("Hq,Hkv,lens", [(4, 2, [1, 17, 128, 129, 200, 333]), (12, 2, [700, 1300, 64]), (2, 1, [2500])])
+def test_attention_bwd_tcgen05(Hq, Hkv, lens):
+    """tcgen05/TMEM backward (attention_bwd_tc.cu) vs autograd through the fp32 oracle."""
+    n = _native()
+    torch.manual_seed(2)
+    D = 128
+    cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32, device="cuda")
+    T = sum(lens)
+    q = torch.randn(T, Hq, D, device="cuda").bfloat16()
+    k = torch.randn(T, Hkv, D, device="cuda").bfloat16()
+    v = torch.randn(T, Hkv, D, device="cuda").bfloat16()
+    sc = 1.0 / math.sqrt(D)
+    o, lse = n.ext().attn_fwd_tc(q, k, v, cu, sc)
+    g = torch.randn_like(o)
+    dq, dk, dv = n.ext().attn_bwd_tc(g, q, k, v, o, lse, cu, sc)
+    qr, kr, vr = (t.float().requires_grad_(True) for t in (q, k, v))
+    ref.attention_varlen(qr, kr, vr, cu.cpu(), causal=True).backward(g.float())
+    for name, a, b in (("dq", dq, qr.grad), ("dk", dk, kr.grad), ("dv", dv, vr.grad)):
+        assert torch.isfinite(a.float()).all(), name
+        assert _rel(a, b) < 3e-2, (name, _rel(a, b))
+
+
 def test_deberta_fused_attention_matches_eager():
     import os
     from nanorlhf_b200.models.deberta_v3 import DebertaV3Config, DebertaV3ForSequenceClassification
