@@ -56,7 +56,14 @@ def attention_varlen(q, k, v, cu_seqlens, max_seqlen=None, causal=True, scale=No
     if impl == "auto":
         impl = "native" if (_native_available() and q.shape[-1] == 128 and q.dtype == torch.bfloat16) else "flash_attn"
     if impl == "native":
-        return _NativeAttn.apply(q.contiguous(), k.contiguous(), v.contiguous(), cu_seqlens.to(torch.int32), max_seqlen, scale)
+        cu = cu_seqlens.to(torch.int32)
+        needs_grad = torch.is_grad_enabled() and (q.requires_grad or k.requires_grad or v.requires_grad)
+        if not needs_grad and _USE_TC and q.shape[-1] == 128:
+            # inference (rollout prefill, log-prob passes): the TMA maps take strided q/k/v views as they are
+            from . import native
+            native._count()
+            return native.ext().attn_fwd_tc(q, k, v, cu, float(scale))[0]
+        return _NativeAttn.apply(q.contiguous(), k.contiguous(), v.contiguous(), cu, max_seqlen, scale)
     if impl == "flash_attn":
         from flash_attn import flash_attn_varlen_func
         cu = cu_seqlens.to(torch.int32)
