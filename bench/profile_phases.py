@@ -60,7 +60,8 @@ if "decode" in which:
 
 if "train" in which:
     policy.train()
-    policy.gradient_checkpointing_enable()
+    if os.environ.get("GC", "1") == "1":
+        policy.gradient_checkpointing_enable()
     pad = shape.vocab_size - 1
     qr = torch.randint(0, 150000, (4, 1650), device=dev)
     params = [p for p in policy.parameters() if p.requires_grad]
@@ -72,6 +73,16 @@ if "train" in which:
     for p in params:
         p.grad = None
     torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    out_lines.append(f"train micro-batch wall (CUDA events, 3 steps): {e0.elapsed_time(e1) / 3:.2f} ms/step")
+    print(out_lines[-1], flush=True)
+    for p in params:
+        p.grad = None
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
         step()
         torch.cuda.synchronize()

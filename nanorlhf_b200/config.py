@@ -123,6 +123,7 @@ class RLConfig:
 
     # ---- runtime (B200) --------------------------------------------------------------------
     comm: str = "fused"                         # fused (symmetric-memory kernels) | nccl
+    train_cuda_graph: str = "auto"              # auto | on | off : replay the micro-step (fwd+loss+bwd) as a CUDA graph
     offload_policy: str = "resident"            # per-role residency: resident | host
     offload_ref: Optional[str] = None
     offload_reward: Optional[str] = None

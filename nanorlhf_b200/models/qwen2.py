@@ -352,6 +352,44 @@ def forward(model, query_responses: torch.Tensor, pad_token_id: int):
     return (out.view(B, L, -1),)
 
 
+def build_logprob_plan(query_responses: torch.Tensor, context_length: int, pad_token_id: int) -> dict:
+    """Host-synchronising part of ``response_logprobs``: packing indices and the (source row -> response slot) map.
+
+    ``src[i]`` is the packed position whose hidden state predicts ``targets[i]``; the result lands in
+    slot ``(r[i], c[i])`` of the [B, T_r] output.
+    """
+    B, L = query_responses.shape
+    ids, cu, pos, mx, flat = pack_padded(query_responses, pad_token_id)
+    # packed token at flat position (b, l) predicts target (b, l+1); needed when l+1 >= ctx
+    col = flat % L
+    row = flat // L
+    nxt_flat = torch.empty_like(flat)
+    nxt_flat[:-1] = flat[1:]
+    nxt_flat[-1] = -1
+    # the next *packed* token must be the next column of the same row (responses are contiguous)
+    pred = (nxt_flat == flat + 1) & (col + 1 < L) & (col + 1 >= context_length)
+    src = pred.nonzero(as_tuple=False).squeeze(1)
+    targets = query_responses.reshape(-1)[flat[src] + 1]
+    return {"ids": ids, "cu": cu, "pos": pos, "max_seqlen": mx, "flat": flat, "col": col, "row": row, "src": src,
+            "targets": targets, "r": row[src], "c": col[src] + 1 - context_length}
+
+
+def planned_response_logprobs(lm, plan: dict, B: int, T_r: int, temperature: float, want_entropy: bool,
+                              invalid_value: float = 1.0, max_seqlen=None, hidden=None):
+    """Device-only part of ``response_logprobs`` (no host sync: CUDA-graph capturable).  ``plan`` may be padded:
+    extra ``src`` entries must carry ``r == B`` (a dump row that is sliced off)."""
+    dev = plan["ids"].device
+    if hidden is None:
+        hidden = lm.hidden_states(plan["ids"], plan["cu"], plan["pos"], max_seqlen or plan["max_seqlen"])
+    logp, ent = lm.token_logprobs(hidden.index_select(0, plan["src"]), plan["targets"], temperature, want_entropy)
+    out_lp = torch.full((B + 1, T_r), invalid_value, dtype=torch.float32, device=dev)
+    out_lp = out_lp.index_put((plan["r"], plan["c"]), logp)[:B]
+    out_ent = torch.zeros((B + 1, T_r), dtype=torch.float32, device=dev)
+    if ent is not None:
+        out_ent = out_ent.index_put((plan["r"], plan["c"]), ent)
+    return out_lp, out_ent[:B], hidden
+
+
 def response_logprobs(lm, query_responses: torch.Tensor, context_length: int, pad_token_id: int,
                       temperature: float, want_entropy: bool = False, invalid_value: float = 1.0,
                       value_model=None):
@@ -369,27 +407,12 @@ def response_logprobs(lm, query_responses: torch.Tensor, context_length: int, pa
     B, L = query_responses.shape
     T_r = L - context_length
     dev = query_responses.device
-    ids, cu, pos, mx, flat = pack_padded(query_responses, pad_token_id)
-    hidden = lm.hidden_states(ids, cu, pos, mx)
-    # packed token at flat position (b, l) predicts target (b, l+1); needed when l+1 >= ctx
-    col = flat % L
-    row = flat // L
-    nxt_flat = torch.empty_like(flat)
-    nxt_flat[:-1] = flat[1:]
-    nxt_flat[-1] = -1
-    # the next *packed* token must be the next column of the same row (responses are contiguous)
-    pred = (nxt_flat == flat + 1) & (col + 1 < L) & (col + 1 >= context_length)
-    src = pred.nonzero(as_tuple=False).squeeze(1)
-    targets = query_responses.reshape(-1)[flat[src] + 1]
-    logp, ent = lm.token_logprobs(hidden[src], targets, temperature, want_entropy)
-    out_lp = torch.full((B, T_r), invalid_value, dtype=torch.float32, device=dev)
-    out_ent = torch.zeros((B, T_r), dtype=torch.float32, device=dev)
-    r = row[src]
-    c = col[src] + 1 - context_length
-    out_lp = out_lp.index_put((r, c), logp)
-    out_ent = out_ent.index_put((r, c), ent)
+    plan = build_logprob_plan(query_responses, context_length, pad_token_id)
+    out_lp, out_ent, hidden = planned_response_logprobs(lm, plan, B, T_r, temperature, want_entropy, invalid_value)
     result = [out_lp, out_ent]
     if value_model is not None:
+        col, row = plan["col"], plan["row"]
+        ids, cu, pos, mx = plan["ids"], plan["cu"], plan["pos"], plan["max_seqlen"]
         vsel = ((col >= context_length - 1) & (col <= L - 2)).nonzero(as_tuple=False).squeeze(1)
         vhidden = hidden if value_model is lm else value_model.hidden_states(ids, cu, pos, mx)
         vals = value_model.values(vhidden[vsel])

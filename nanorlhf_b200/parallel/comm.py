@@ -81,9 +81,20 @@ class Comm:
         if self.world_size == 1:
             return t
         t = t.contiguous()
+        if t.dim() == 0:
+            t = t.reshape(1)
+        # leading sizes may differ per rank (e.g. the number of micro-buckets under data-dependent batching):
+        # agree on them first, pad to the longest, trim after the gather
+        n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
+        sizes = [torch.empty_like(n) for _ in range(self.world_size)]
+        dist.all_gather(sizes, n)
+        sizes = [int(x.item()) for x in sizes]
+        mx = max(sizes)
+        if t.shape[0] < mx:
+            t = torch.cat([t, t.new_zeros((mx - t.shape[0],) + tuple(t.shape[1:]))], 0)
         out = [torch.empty_like(t) for _ in range(self.world_size)]
         dist.all_gather(out, t)
-        return torch.cat([o.reshape(-1) if o.dim() == 0 else o for o in out], 0)
+        return torch.cat([o[:k] for o, k in zip(out, sizes)], 0)
 
     def broadcast_(self, t: torch.Tensor, src: int = 0) -> torch.Tensor:
         if self.world_size > 1:

@@ -400,13 +400,30 @@ class RLTrainer:
         m._nrl_version = getattr(m, "_nrl_version", 0) + 1
 
     # ---- phase 6 ------------------------------------------------------------------------------
+    def _graph_micro_step(self):
+        """CUDA-graph replay of the micro-step (trainer/graphed.py) when the step is graph-safe."""
+        a = self.args
+        mode = getattr(a, "train_cuda_graph", "auto")
+        ok = (self.device.type == "cuda" and mode != "off" and not self.uses_value_model and a.lora_dropout == 0.0
+              and ops.use_native(torch.empty(0, device=self.device)))
+        if mode == "auto":
+            ok = ok and not a.gradient_checkpointing           # torch.utils.checkpoint is not captured
+        if not ok:
+            return None
+        if getattr(self, "_graphed", None) is None:
+            from .graphed import GraphedMicroStep
+            self._graphed = GraphedMicroStep(self)
+        return self._graphed
+
     def optimise(self, batch) -> Dict[str, torch.Tensor]:
         a = self.args
         ctx = batch["context_length"]
         pad = self.tokenizer.pad_token_id
         shape = (a.num_ppo_epochs, a.num_mini_batches, a.gradient_accumulation_steps)
-        stats = defaultdict(lambda: torch.zeros(shape, device=self.device))
         n_local = batch["responses"].shape[0]
+        graphed = self._graph_micro_step()
+        keys = graphed.stat_keys if graphed is not None else None
+        rows = {}
         self.policy.train()
         for ep in range(a.num_ppo_epochs):
             b_inds = self._np_rng.permutation(n_local)
@@ -417,6 +434,10 @@ class RLTrainer:
                     inds = torch.as_tensor(mini[mc_start:mc_start + a.per_device_train_batch_size], device=self.device)
                     mb = {k: (v[inds] if isinstance(v, torch.Tensor) and v.dim() > 0 and v.shape[0] == n_local else v)
                           for k, v in batch.items()}
+                    if graphed is not None:
+                        rows[(ep, mi, gi)] = graphed(mb, ctx, pad)
+                        keys = graphed.stat_keys
+                        continue
                     out = response_logprobs(self.policy, mb["query_responses"], ctx, pad, a.temperature,
                                             want_entropy=True,
                                             value_model=self.model.value_model if self.uses_value_model else None)
@@ -433,10 +454,19 @@ class RLTrainer:
                         else:
                             m = (~mb["padding_mask"]).float()
                             st["entropy"] = (ent * m).sum() / m.sum().clamp_min(1)
-                        for k, v in st.items():
-                            stats[k][ep, mi, gi] = v
+                        if keys is None:
+                            keys = sorted(st)
+                        rows[(ep, mi, gi)] = torch.stack([st[k].detach().float().reshape(()) for k in keys])
                 self.optimizer.step()
         self.optimizer.zero_grad()
+        # one [E, M, G, n_stats] tensor, sliced per statistic (slots that never ran stay zero)
+        stats = defaultdict(lambda: torch.zeros(shape, device=self.device))
+        if rows:
+            table = torch.zeros(shape + (len(keys),), device=self.device)
+            idx = torch.as_tensor(list(rows.keys()), device=self.device)
+            table[idx[:, 0], idx[:, 1], idx[:, 2]] = torch.stack(list(rows.values()))
+            for i, k in enumerate(keys):
+                stats[k] = table[..., i]
         return stats
 
     # ---- metrics ------------------------------------------------------------------------------

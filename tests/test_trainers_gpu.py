@@ -60,3 +60,59 @@ def test_algorithm_on_native_backend(name, extra, kw, tmp_path):
             assert v == v and abs(v) < 1e9, (k, v)
     assert all(torch.isfinite(p).all() for p in t.policy.parameters())
     assert os.path.isdir(os.path.join(str(tmp_path), "checkpoint-2"))
+
+
+def test_graphed_micro_step_matches_eager(tmp_path):
+    """CUDA-graph replay of fwd+loss+bwd (trainer/graphed.py) reproduces the eager micro-step: stats and gradients."""
+    from nanorlhf_b200.trainer import GRPOTrainer
+    from nanorlhf_b200.trainer.graphed import GraphedMicroStep
+    t = _setup(tmp_path, GRPOTrainer, {"grpo_sample_N": 4}, gradient_checkpointing=False, train_cuda_graph="on")
+    assert t._graph_micro_step() is not None
+    dev, pad = t.device, t.tokenizer.pad_token_id
+    B, ctx, T_r = 2, 12, 24
+    gen = torch.Generator(device="cpu").manual_seed(0)
+
+    def make_mb(qlens, rlens):
+        qr = torch.full((B, ctx + T_r), pad, dtype=torch.long)
+        pm = torch.ones(B, T_r, dtype=torch.bool)
+        for b, (ql, rl) in enumerate(zip(qlens, rlens)):
+            qr[b, ctx - ql:ctx + rl] = torch.randint(0, 4000, (ql + rl,), generator=gen)
+            pm[b, :rl] = False
+        f = lambda: torch.randn(B, T_r, generator=gen) * 0.1 - 2.0                                   # noqa: E731
+        return {"query_responses": qr.to(dev), "padding_mask": pm.to(dev), "logprobs": f().to(dev),
+                "ref_logprobs": f().to(dev), "advantages": torch.randn(B, T_r, generator=gen).to(dev),
+                "context_length": ctx}
+
+    params = [p for p in t.policy.parameters() if p.requires_grad]
+
+    def run(step, mb):
+        t.optimizer.zero_grad()
+        vec = step(mb, ctx, pad).clone()
+        return vec, torch.cat([p.grad.detach().float().reshape(-1) for p in params]).clone()
+
+    t.policy.train()
+    g = GraphedMicroStep(t)
+    mb1, mb2 = make_mb([5, 9], [24, 17]), make_mb([7, 8], [20, 20])          # same bucket, different data
+    v_eager, g_eager = run(g, mb1)                                           # first sight of the bucket: eager
+    v_graph, g_graph = run(g, mb1)                                           # capture + replay
+    assert g.replays == 1 and g.eager == 1
+    assert torch.allclose(v_eager, v_graph, rtol=1e-4, atol=1e-5), (v_eager, v_graph)
+    assert (g_eager - g_graph).abs().max() <= 1e-3 * g_eager.abs().max() + 1e-7
+    v2_graph, g2_graph = run(g, mb2)                                         # pure replay on new data
+    v2_eager, g2_eager = run(GraphedMicroStep(t), mb2)                       # a fresh instance runs eagerly
+    assert g.replays == 2
+    assert torch.allclose(v2_eager, v2_graph, rtol=1e-4, atol=1e-5)
+    assert (g2_eager - g2_graph).abs().max() <= 1e-3 * g2_eager.abs().max() + 1e-7
+    assert g2_eager.abs().max() > 0
+
+
+def test_grpo_trains_with_cuda_graph_micro_steps(tmp_path):
+    from nanorlhf_b200.trainer import GRPOTrainer
+    t = _setup(tmp_path, GRPOTrainer, {"grpo_sample_N": 4}, gradient_checkpointing=False, train_cuda_graph="on",
+               total_episodes=32)
+    m = t.train()
+    assert t._graphed is not None and t._graphed.replays > 0
+    for k, v in m.items():
+        if isinstance(v, float):
+            assert v == v and abs(v) < 1e9, (k, v)
+    assert all(torch.isfinite(p).all() for p in t.policy.parameters())
