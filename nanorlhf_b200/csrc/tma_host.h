@@ -25,6 +25,10 @@ inline PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
 // box_cols * elem_bytes must be 128 (one swizzle row).
 inline CUtensorMap make_tma_2d(const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_bytes,
                                uint32_t box_rows, uint32_t box_cols, CUtensorMapDataType dtype, int elem_bytes) {
+  // The driver call needs the primary context current on THIS thread.  Autograd worker threads only get it once a
+  // runtime-API call has run there, and the caching allocator can satisfy torch::empty without one.
+  thread_local bool ctx_bound = (cudaFree(nullptr) == cudaSuccess);
+  (void)ctx_bound;
   CUtensorMap m;
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {row_stride_bytes};
