@@ -41,6 +41,19 @@ if which in ("all", "attn"):
     v = torch.randn(T, 2, 128, device=dev, dtype=torch.bfloat16)
     for _ in range(2):
         native.ext().attn_varlen_fwd(q, k, v, cu, 1650, 1 / math.sqrt(128), True)
+if which in ("all", "deberta"):
+    from nanorlhf_b200.models.deberta_v3 import build_bucket_lut
+    lens = [1660] * 8
+    cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), device=dev, dtype=torch.int32)
+    T = sum(lens)
+    q = torch.randn(T, 16, 64, device=dev, dtype=torch.bfloat16)
+    k = torch.randn(T, 16, 64, device=dev, dtype=torch.bfloat16)
+    v = torch.randn(T, 16, 64, device=dev, dtype=torch.bfloat16)
+    ra = torch.randn(16, T, 512, device=dev, dtype=torch.bfloat16)
+    rb = torch.randn(16, T, 512, device=dev, dtype=torch.bfloat16)
+    lut = build_bucket_lut(1660, 256, 512, 256, dev)
+    for _ in range(2):
+        native.ext().attn_varlen_fwd(q, k, v, cu, 1660, 1 / math.sqrt(192), False, ra, rb, lut)
 if which in ("all", "attn_tc"):
     lens = [4096] * 4
     cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), device=dev, dtype=torch.int32)

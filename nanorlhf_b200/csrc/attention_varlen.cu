@@ -90,7 +90,8 @@ NRL_DEVICE void load_tile_async(uint8_t* smem_tile, const __nv_bfloat16* base, l
   }
 }
 
-constexpr int kRelBW = 112;   // staged window of the key-side bias table: >= 64 + 32 - 1 + 7, multiple of 8
+constexpr int kRelBW = 112;   // staged window of the bias tables: >= 64 + 32 - 1 + 7 columns, multiple of 8
+constexpr int kRelStride = 120;   // smem row stride of a window (elements): 240 B = 60 words -> rows land 28 banks apart
 
 // first (8-aligned) table column needed by the score tile (rows q0..q0+63, keys k0..k0+BN-1)
 NRL_DEVICE int rel_window_lo(const AttnParams& p, int q0, int k0, int BN) {
@@ -108,8 +109,8 @@ __global__ void __launch_bounds__(128) flash_fwd_kernel(AttnParams p) {
   uint8_t* sQ = smem;                              // [64][D]
   uint8_t* sK = sQ + BM * D * 2;                   // [2][BN][D]
   uint8_t* sV = sK + 2 * BN * D * 2;               // [2][BN][D]
-  uint8_t* sA = sV + 2 * BN * D * 2;               // REL_BIAS: [64][NB] bf16
-  uint8_t* sB = sA + (REL_BIAS ? BM * p.NB * 2 : 0);   // REL_BIAS: [2][BN][kRelBW] bf16 (column window, see below)
+  uint8_t* sA = sV + 2 * BN * D * 2;               // REL_BIAS: [2][BM][kRelStride] bf16 (column window, see below)
+  uint8_t* sB = sA + (REL_BIAS ? 2 * BM * kRelStride * 2 : 0);   // REL_BIAS: [2][BN][kRelStride] bf16
 
   int seq, m_blk, seq_start, seq_len;
   if (!locate_block<BM>(p.cu_seqlens, p.num_seqs, blockIdx.x, seq, m_blk, seq_start, seq_len)) return;
@@ -123,30 +124,33 @@ __global__ void __launch_bounds__(128) flash_fwd_kernel(AttnParams p) {
   const __nv_bfloat16* vbase = p.v + static_cast<long>(seq_start) * p.v_stride_t;
 
   load_tile_async<D, BM, 128>(sQ, qbase, p.q_stride_t, head, q0, seq_len);
-  if (REL_BIAS) {
-    const int CH = p.NB / 8;
-    const __nv_bfloat16* abase = p.rel_a + (static_cast<long>(head) * p.total_tokens + seq_start) * p.NB;
-    for (int i = threadIdx.x; i < BM * CH; i += 128) {
-      const int r = i / CH, c = i % CH;
-      const bool ok = (q0 + r) < seq_len;
-      cp_async_16_zfill(sA + (static_cast<long>(r) * p.NB + c * 8) * 2, abase + static_cast<long>(ok ? q0 + r : q0) * p.NB + c * 8, ok);
-    }
-  }
   auto load_kv = [&](int nb, int buf) {
     load_tile_async<D, BN, 128>(sK + buf * BN * D * 2, kbase, p.k_stride_t, kvh, nb * BN, seq_len);
     load_tile_async<D, BN, 128>(sV + buf * BN * D * 2, vbase, p.v_stride_t, kvh, nb * BN, seq_len);
     if (REL_BIAS) {
       // The bucket index c(i-j) is monotone in (i-j) with slope <= 1, so a (64 x BN) score tile touches at
-      // most 64+BN-1 consecutive table columns: stage only that window of B (not all NB columns).
+      // most 64+BN-1 consecutive table columns: stage only that window of A (query rows) and B (key rows).
+      // (Windowing A as well as B keeps the CTA at ~70 KB of smem: 3 CTAs / SM instead of 2.)
       const int CH = kRelBW / 8;
       const int c_lo = rel_window_lo(p, q0, nb * BN, BN);
-      const __nv_bfloat16* bbase = p.rel_b + (static_cast<long>(head) * p.total_tokens + seq_start) * p.NB;
-      uint8_t* dst = sB + static_cast<long>(buf) * BN * kRelBW * 2;
-      for (int i = threadIdx.x; i < BN * CH; i += 128) {
+      const long tbase = (static_cast<long>(head) * p.total_tokens + seq_start) * p.NB;
+      const __nv_bfloat16* abase = p.rel_a + tbase;
+      const __nv_bfloat16* bbase = p.rel_b + tbase;
+      uint8_t* dst_a = sA + static_cast<long>(buf) * BM * kRelStride * 2;
+      uint8_t* dst_b = sB + static_cast<long>(buf) * BN * kRelStride * 2;
+      for (int i = threadIdx.x; i < (BM + BN) * CH; i += 128) {
         const int r = i / CH, c = i % CH;
-        const bool ok = ((nb * BN + r) < seq_len) && (c_lo + c * 8 < p.NB);
-        cp_async_16_zfill(dst + (static_cast<long>(r) * kRelBW + c * 8) * 2,
-                          bbase + static_cast<long>(ok ? nb * BN + r : nb * BN) * p.NB + (ok ? c_lo + c * 8 : 0), ok);
+        const bool col_ok = c_lo + c * 8 < p.NB;
+        if (r < BM) {
+          const bool ok = ((q0 + r) < seq_len) && col_ok;
+          cp_async_16_zfill(dst_a + (static_cast<long>(r) * kRelStride + c * 8) * 2,
+                            abase + static_cast<long>(ok ? q0 + r : q0) * p.NB + (ok ? c_lo + c * 8 : 0), ok);
+        } else {
+          const int rb = r - BM;
+          const bool ok = ((nb * BN + rb) < seq_len) && col_ok;
+          cp_async_16_zfill(dst_b + (static_cast<long>(rb) * kRelStride + c * 8) * 2,
+                            bbase + static_cast<long>(ok ? nb * BN + rb : nb * BN) * p.NB + (ok ? c_lo + c * 8 : 0), ok);
+        }
       }
     }
   };
@@ -195,19 +199,19 @@ __global__ void __launch_bounds__(128) flash_fwd_kernel(AttnParams p) {
       const short* lut = p.bucket_lut + p.lut_center;
       const int dmin = max(q0 - (key0 + BN - 1), -p.lut_center), dmax = min(q0 + BM - 1 - key0, p.lut_center);
       const int c_min = lut[dmin], c_max = lut[dmax];
-      const __nv_bfloat16* aw = reinterpret_cast<const __nv_bfloat16*>(sA);
-      const __nv_bfloat16* bw = reinterpret_cast<const __nv_bfloat16*>(sB + static_cast<long>(buf) * BN * kRelBW * 2);
-      const __nv_bfloat16* ar_a = aw + static_cast<long>(row_a - q0) * p.NB;
-      const __nv_bfloat16* ar_b = aw + static_cast<long>(row_b - q0) * p.NB;
+      const __nv_bfloat16* aw = reinterpret_cast<const __nv_bfloat16*>(sA + static_cast<long>(buf) * BM * kRelStride * 2);
+      const __nv_bfloat16* bw = reinterpret_cast<const __nv_bfloat16*>(sB + static_cast<long>(buf) * BN * kRelStride * 2);
+      const __nv_bfloat16* ar_a = aw + static_cast<long>(row_a - q0) * kRelStride;
+      const __nv_bfloat16* ar_b = aw + static_cast<long>(row_b - q0) * kRelStride;
       if (c_min == c_max) {
         // far-from-diagonal tile: one bucket for every (i, j) -> bias = A[i, c0] + B[j, c0] (rank-1, no lookups)
-        const float a0 = __bfloat162float(ar_a[c_min]), a1 = __bfloat162float(ar_b[c_min]);
         const int cw = c_min - c_lo_cur;
+        const float a0 = __bfloat162float(ar_a[cw]), a1 = __bfloat162float(ar_b[cw]);
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) {
           const int kl = nt * 8 + t4 * 2;
-          const float b0 = __bfloat162float(bw[static_cast<long>(kl) * kRelBW + cw]);
-          const float b1 = __bfloat162float(bw[static_cast<long>(kl + 1) * kRelBW + cw]);
+          const float b0 = __bfloat162float(bw[static_cast<long>(kl) * kRelStride + cw]);
+          const float b1 = __bfloat162float(bw[static_cast<long>(kl + 1) * kRelStride + cw]);
           s[nt][0] += a0 + b0; s[nt][1] += a0 + b1; s[nt][2] += a1 + b0; s[nt][3] += a1 + b1;
         }
       } else {
@@ -219,9 +223,9 @@ __global__ void __launch_bounds__(128) flash_fwd_kernel(AttnParams p) {
             const int row = (e < 2) ? row_a : row_b;
             // rows/keys of the padded tail of the last block fall outside the table: clamp (their scores are masked)
             const int c = lut[min(max(row - key0 - kl, -p.lut_center), p.lut_center)];
+            const int cw = min(max(c - c_lo_cur, 0), kRelBW - 1);
             const __nv_bfloat16* ar = (e < 2) ? ar_a : ar_b;
-            s[nt][e] += __bfloat162float(ar[c]) +
-                        __bfloat162float(bw[static_cast<long>(kl) * kRelBW + min(max(c - c_lo_cur, 0), kRelBW - 1)]);
+            s[nt][e] += __bfloat162float(ar[cw]) + __bfloat162float(bw[static_cast<long>(kl) * kRelStride + cw]);
           }
       }
     }
@@ -802,7 +806,7 @@ extern "C" cudaError_t nrl_attn_varlen_fwd(const void* q, const void* k, const v
   if (rel_a != nullptr) {
     if (D != 64 || causal) return cudaErrorInvalidValue;
     constexpr int BN = 32;
-    const int smem = 64 * 64 * 2 + 4 * BN * 64 * 2 + 64 * NB * 2 + 2 * BN * kRelBW * 2;
+    const int smem = 64 * 64 * 2 + 4 * BN * 64 * 2 + 2 * (64 + BN) * kRelStride * 2;
     auto kern = flash_fwd_kernel<64, false, true, BN>;
     if ((e = set_smem(kern, smem)) != cudaSuccess) return e;
     kern<<<grid, 128, smem, s>>>(p);
