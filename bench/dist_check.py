@@ -133,8 +133,9 @@ def main():
         with open(os.path.join(ROOT, "gpurun_out", f"dist_check_{W}.json"), "w") as fh:
             json.dump(res, fh, indent=1)
         print(json.dumps(res), flush=True)
-    ok = res["allreduce_max_abs_err"] <= 0.02 * max(res["allreduce_ref_scale"], 1.0) and res["adam_p2p_max_abs_err"] < 2e-2 \
-        and res["adam_p2p_ranks_identical"]
+    # tolerance = a couple of bf16 ulps at the magnitude of the reduced values (the reduction order differs from NCCL's)
+    tol = 0.02 * max(res["allreduce_ref_scale"], 1.0)
+    ok = res["allreduce_max_abs_err"] <= tol and res["adam_p2p_max_abs_err"] <= tol and res["adam_p2p_ranks_identical"]
     comm.barrier()
     comm.close()
     sys.exit(0 if ok else 1)
