@@ -62,5 +62,6 @@ if which in ("all", "attn_tc"):
     k = torch.randn(T, 2, 128, device=dev, dtype=torch.bfloat16)
     v = torch.randn(T, 2, 128, device=dev, dtype=torch.bfloat16)
     for _ in range(2):
-        native.ext().attn_fwd_tc(q, k, v, cu, 1 / math.sqrt(128))
+        o, lse = native.ext().attn_fwd_tc(q, k, v, cu, 1 / math.sqrt(128))
+    native.ext().attn_bwd_tc(torch.randn_like(o), q, k, v, o, lse, cu, 1 / math.sqrt(128))
 torch.cuda.synchronize()
