@@ -81,6 +81,37 @@ def test_packed_forward_equals_padded_semantics():
     assert out[2].shape == lp.shape
 
 
+def test_bucket_padded_plan_gives_the_same_logprobs_and_grads():
+    """trainer/graphed.py pads the packed plan with a dummy sequence and dump-row entries so that the micro-step
+    has a static shape; neither may change the log-probs, the entropies or the gradients."""
+    from nanorlhf_b200.models.qwen2 import build_logprob_plan, planned_response_logprobs
+    from nanorlhf_b200.trainer.graphed import GraphedMicroStep
+    torch.manual_seed(0)
+    m = _tiny()
+    pad, ctx = 96, 4
+    qr = torch.randint(0, 90, (3, 12))
+    qr[0, :3] = pad
+    qr[1, 9:] = pad
+    B, T_r = 3, 12 - ctx
+
+    def run(plan):
+        m.zero_grad()
+        lp, ent, _ = planned_response_logprobs(m, plan, B, T_r, 0.9, True, max_seqlen=12)
+        real = qr[:, ctx:] != pad
+        (lp[real] ** 2).sum().backward()
+        return lp.detach(), ent.detach(), torch.cat([p.grad.reshape(-1) for p in m.parameters()]).clone()
+
+    plan = build_logprob_plan(qr, ctx, pad)
+    T, R = plan["ids"].numel(), plan["src"].numel()
+    lp0, ent0, g0 = run(plan)
+    for T_b, R_b in ((T + 5, R + 7), (T, R)):                 # with and without a dummy sequence
+        padded = GraphedMicroStep._pad_plan(plan, B, pad, T_b, R_b)
+        padded["max_seqlen"] = 12
+        lp1, ent1, g1 = run(padded)
+        assert torch.allclose(lp0, lp1, atol=1e-5) and torch.allclose(ent0, ent1, atol=1e-5)
+        assert torch.allclose(g0, g1, atol=1e-5)
+
+
 def test_save_load_pretrained_roundtrip(tmp_path):
     m = _tiny()
     m.save_pretrained(str(tmp_path))
