@@ -48,6 +48,7 @@ class GraphedMicroStep:
         self.stat_keys: Optional[list] = None
         self.replays = 0
         self.eager = 0
+        self.disabled = False
 
     # ---- the device-only micro-step ---------------------------------------------------------------
     def _body(self, plan, mb, B, T_r, L):
@@ -109,10 +110,18 @@ class GraphedMicroStep:
         if cap is None:
             n = self.seen.get(key, 0)
             self.seen[key] = n + 1
-            if n == 0 or len(self.graphs) >= MAX_GRAPHS:
+            if n == 0 or self.disabled or len(self.graphs) >= MAX_GRAPHS:
                 self.eager += 1
                 return self._body(padded, tens, B, T_r, L)           # eager (also the capture warm-up)
-            cap = self._capture(key, padded, tens, B, T_r, L)
+            try:
+                cap = self._capture(key, padded, tens, B, T_r, L)
+            except Exception as e:  # noqa: BLE001 -- a step that cannot be captured must still train
+                import warnings
+                warnings.warn(f"CUDA-graph capture of the micro-step failed ({type(e).__name__}: {e}); "
+                              "using eager micro-steps from now on")
+                self.disabled = True                  # capture records, it does not execute: .grad is untouched
+                self.eager += 1
+                return self._body(padded, tens, B, T_r, L)
         else:
             self.graphs.move_to_end(key)
         for k, v in padded.items():
