@@ -37,11 +37,21 @@ int num_sms() {
   return n;
 }
 
-int pick_block_n(int64_t M, int64_t N) {
-  // 256-wide tiles unless that leaves most SMs idle
-  int64_t tiles256 = ((M + 127) / 128) * ((N + 255) / 256);
-  if (N <= 128 || tiles256 < num_sms() / 2) return 128;
-  return 256;
+int pick_block_n(int64_t M, int64_t N, bool allow_192 = false) {
+  // score = (SM occupancy of the last wave) x (useful fraction of the padded N) x (per-tile efficiency of the shape)
+  const int sms = num_sms();
+  const int64_t num_m = (M + 127) / 128;
+  auto score = [&](int bn, double tile_eff) {
+    const int64_t num_n = (N + bn - 1) / bn, tiles = num_m * num_n;
+    const int64_t waves = (tiles + sms - 1) / sms;
+    return tile_eff * static_cast<double>(tiles) / static_cast<double>(waves * sms) * static_cast<double>(N) /
+           static_cast<double>(num_n * bn);
+  };
+  int best = 256;
+  double best_s = score(256, 1.0);
+  if (allow_192 && score(192, 0.95) > best_s) { best = 192; best_s = score(192, 0.95); }
+  if (N <= 128 || score(128, 0.82) > best_s) best = 128;
+  return best;
 }
 
 // D[M,N] = A[M,K] @ B[N,K]^T (+ bias[N])
@@ -57,7 +67,7 @@ torch::Tensor gemm_bf16(const torch::Tensor& a, const torch::Tensor& b, const c1
   check_bf16_2d(out, "out");
   TORCH_CHECK(out.size(0) == M && out.size(1) == N, "out has the wrong shape");
   if (M == 0) return out;
-  const int bn = block_n > 0 ? static_cast<int>(block_n) : pick_block_n(M, N);
+  const int bn = block_n > 0 ? static_cast<int>(block_n) : pick_block_n(M, N, /*allow_192=*/true);
   CUtensorMap tmA = nrl::make_tma_2d(a.data_ptr(), M, K, a.stride(0) * 2, 128, 64, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2);
   CUtensorMap tmB = nrl::make_tma_2d(b.data_ptr(), N, K, b.stride(0) * 2, bn, 64, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2);
   CUtensorMap tmD = nrl::make_tma_2d(out.data_ptr(), M, N, out.stride(0) * 2, 128, 64, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2);

@@ -36,7 +36,7 @@ struct SmemLayout {
   static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
   static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BLOCK_N == 256) ? 4 : 6;
+  static constexpr int kStages = (BLOCK_N >= 192) ? 4 : 6;
   static constexpr int kStagingOff = kStages * kStageBytes;
   static constexpr int kBarOff = kStagingOff + 2 * kStagingBytes;
   static constexpr int kTotal = kBarOff + 256;
@@ -83,7 +83,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int n_splits = (EPI == EPI_LOGPROB) ? p.n_splits : 1;
   const int n_per_split = (EPI == EPI_LOGPROB) ? (num_n_total + n_splits - 1) / n_splits : 1;
   const int num_work = (EPI == EPI_LOGPROB) ? num_m * n_splits : num_m * num_n_total;
-  constexpr uint32_t kTmemCols = 2 * BLOCK_N;
+  constexpr uint32_t kTmemCols = (2 * BLOCK_N <= 256) ? 256 : 512;      // power of two >= two accumulators
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -448,6 +448,9 @@ extern "C" cudaError_t nrl_gemm_bf16_tn(const CUtensorMap* tmA, const CUtensorMa
     if (epi == EPI_DLOGITS) return launch_impl<256, EPI_DLOGITS>(*tmA, *tmB, *tmD, *p, num_sms, stream);
     if (epi == EPI_MERGE) return launch_impl<256, EPI_MERGE>(*tmA, *tmB, *tmD, *p, num_sms, stream);
     if (epi == EPI_SWIGLU) return launch_impl<256, EPI_SWIGLU>(*tmA, *tmB, *tmD, *p, num_sms, stream);
+  } else if (block_n == 192) {
+    // 192-wide tiles: N = 1536-class outputs (o_proj / down_proj) fill 128 of 148 SMs at M = 2048 instead of 96
+    if (epi == EPI_STORE) return launch_impl<192, EPI_STORE>(*tmA, *tmB, *tmD, *p, num_sms, stream);
   } else if (block_n == 128) {
     if (epi == EPI_SWIGLU) return launch_impl<128, EPI_SWIGLU>(*tmA, *tmB, *tmD, *p, num_sms, stream);
     if (epi == EPI_MERGE) return launch_impl<128, EPI_MERGE>(*tmA, *tmB, *tmD, *p, num_sms, stream);

@@ -20,7 +20,7 @@ def _rel(a, b):
 
 
 @pytest.mark.parametrize("M,N,K,bn", [(128, 256, 64, 256), (256, 512, 1536, 256), (2048, 2048, 1536, 0), (300, 1536, 8960, 0),
-                                       (6800, 17920, 1536, 0), (77, 136, 200, 128), (4096, 1536, 1536, 128)])
+                                       (6800, 17920, 1536, 0), (77, 136, 200, 128), (4096, 1536, 1536, 128), (2048, 1536, 8960, 192), (300, 200, 264, 192)])
 def test_gemm_bf16(M, N, K, bn):
     n = _native()
     torch.manual_seed(0)
