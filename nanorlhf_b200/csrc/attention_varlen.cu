@@ -38,6 +38,13 @@ NRL_DEVICE uint32_t tile_off(int r, int c) {
   return static_cast<uint32_t>(r * (D * 2) + ((c ^ (r & 7)) << 4));
 }
 
+// one bf16 from shared memory (32-bit shared address) as fp32
+NRL_DEVICE float lds_bf16(uint32_t addr) {
+  unsigned short h;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(addr));
+  return __uint_as_float(static_cast<uint32_t>(h) << 16);
+}
+
 struct AttnParams {
   const __nv_bfloat16 *q, *k, *v, *o, *dout;
   __nv_bfloat16 *out, *dq, *dk, *dv;
@@ -215,30 +222,46 @@ __global__ void __launch_bounds__(128) flash_fwd_kernel(AttnParams p) {
           s[nt][0] += a0 + b0; s[nt][1] += a0 + b1; s[nt][2] += a1 + b0; s[nt][3] += a1 + b1;
         }
       } else {
+        // General tile: one LUT read + two table reads per score.  Everything is 32-bit shared-memory addressing
+        // with compile-time offsets; the thread's second row (row_a + 8) sees the deltas of the first row shifted
+        // by one 8-key group, so its bucket indices are reused (10 LUT reads per thread instead of 16).
+        // The LUT carries a 64-entry margin on both sides (build_bucket_lut), so padded-tail rows/keys stay in range;
+        // their window offsets are clamped by the unsigned min below and their scores are masked.
+        const short* lut_row = lut + (row_a - key0 - t4 * 2);
+        uint32_t cw2[NT + 1][2];                      // 2 * (bucket - window start) of row_a at key group nt-1, parity e1
+#pragma unroll
+        for (int g8 = 0; g8 <= NT; ++g8)
+#pragma unroll
+          for (int e1 = 0; e1 < 2; ++e1) {
+            const int c = lut_row[-((g8 - 1) * 8 + e1)];
+            cw2[g8][e1] = min(static_cast<uint32_t>(c - c_lo_cur), static_cast<uint32_t>(kRelBW - 1)) * 2u;
+          }
+        const uint32_t sa_a = smem_u32(aw) + static_cast<uint32_t>(row_a - q0) * (kRelStride * 2);
+        const uint32_t sa_b = sa_a + 8 * kRelStride * 2;
+        const uint32_t sb0 = smem_u32(bw) + static_cast<uint32_t>(t4 * 2) * (kRelStride * 2);
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int kl = nt * 8 + t4 * 2 + (e & 1);
-            const int row = (e < 2) ? row_a : row_b;
-            // rows/keys of the padded tail of the last block fall outside the table: clamp (their scores are masked)
-            const int c = lut[min(max(row - key0 - kl, -p.lut_center), p.lut_center)];
-            const int cw = min(max(c - c_lo_cur, 0), kRelBW - 1);
-            const __nv_bfloat16* ar = (e < 2) ? ar_a : ar_b;
-            s[nt][e] += __bfloat162float(ar[cw]) + __bfloat162float(bw[static_cast<long>(kl) * kRelStride + cw]);
+          for (int e1 = 0; e1 < 2; ++e1) {
+            const uint32_t brow = sb0 + (nt * 8 + e1) * (kRelStride * 2);
+            const uint32_t wa = cw2[nt + 1][e1], wb = cw2[nt][e1];
+            s[nt][e1] += lds_bf16(sa_a + wa) + lds_bf16(brow + wa);
+            s[nt][2 + e1] += lds_bf16(sa_b + wb) + lds_bf16(brow + wb);
           }
       }
     }
+    // ---- mask: only blocks that cross the end of the sequence (or the causal diagonal) have dead entries ----
+    if ((key0 + BN > seq_len) || (CAUSAL && key0 + BN - 1 > q0)) {
 #pragma unroll
-    for (int nt = 0; nt < NT; ++nt)
+      for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int key = key0 + nt * 8 + t4 * 2 + (e & 1);
-        const int row = (e < 2) ? row_a : row_b;
-        const bool dead = (key >= seq_len) || (CAUSAL && key > row);
-        s[nt][e] = dead ? -INFINITY : s[nt][e] * p.scale_log2;
-      }
-    // ---- online softmax (rows a = c0,c1 ; b = c2,c3) ----
+        for (int e = 0; e < 4; ++e) {
+          const int key = key0 + nt * 8 + t4 * 2 + (e & 1);
+          const int row = (e < 2) ? row_a : row_b;
+          if ((key >= seq_len) || (CAUSAL && key > row)) s[nt][e] = -INFINITY;
+        }
+    }
+    // ---- online softmax (rows a = c0,c1 ; b = c2,c3); scores stay unscaled, the scale rides in the exp2 FMA ----
     float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
@@ -253,8 +276,9 @@ __global__ void __launch_bounds__(128) flash_fwd_kernel(AttnParams p) {
     float corr[2], ps[2] = {0.f, 0.f};
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
-      const float mn = fmaxf(m_run[r], mx[r]);
-      corr[r] = (mn == -INFINITY) ? 1.f : exp2f(m_run[r] - mn);
+      // key 0 is live for every row (also for the causal case), so mn is finite from the first block on
+      const float mn = fmaxf(m_run[r], mx[r] * p.scale_log2);
+      corr[r] = exp2f(m_run[r] - mn);
       m_run[r] = mn;
     }
 #pragma unroll
@@ -262,7 +286,7 @@ __global__ void __launch_bounds__(128) flash_fwd_kernel(AttnParams p) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int r = e >> 1;
-        const float pv = (m_run[r] == -INFINITY) ? 0.f : exp2f(s[nt][e] - m_run[r]);
+        const float pv = exp2f(fmaf(s[nt][e], p.scale_log2, -m_run[r]));
         s[nt][e] = pv;
         ps[r] += pv;
       }
@@ -298,6 +322,214 @@ __global__ void __launch_bounds__(128) flash_fwd_kernel(AttnParams p) {
   cp_async_wait<0>();
 
   // ---- epilogue ----
+  const float inv_a = l_run[0] > 0.f ? 1.f / l_run[0] : 0.f, inv_b = l_run[1] > 0.f ? 1.f / l_run[1] : 0.f;
+  __nv_bfloat16* obase = p.out + static_cast<long>(seq_start) * p.o_stride_t + head * D;
+#pragma unroll
+  for (int i = 0; i < D / 8; ++i) {
+    const int col = i * 8 + t4 * 2;
+    if (row_a < seq_len)
+      *reinterpret_cast<uint32_t*>(obase + static_cast<long>(row_a) * p.o_stride_t + col) = pack_bf16x2(o[i][0] * inv_a, o[i][1] * inv_a);
+    if (row_b < seq_len)
+      *reinterpret_cast<uint32_t*>(obase + static_cast<long>(row_b) * p.o_stride_t + col) = pack_bf16x2(o[i][2] * inv_b, o[i][3] * inv_b);
+  }
+  if (p.lse != nullptr && t4 == 0) {
+    const float ln2 = 0.6931471805599453f;
+    float* lse = p.lse + static_cast<long>(head) * p.total_tokens + seq_start;
+    if (row_a < seq_len) lse[row_a] = (m_run[0] + log2f(l_run[0])) * ln2;
+    if (row_b < seq_len) lse[row_b] = (m_run[1] + log2f(l_run[1])) * ln2;
+  }
+}
+
+// =================================================================================================
+// DeBERTa disentangled attention, TMA-fed (K8).  Same math as flash_fwd_kernel<64, false, true, 32>, but every
+// tile -- Q, K_j, V_j and the two sliding bias-table windows -- arrives by TMA behind one mbarrier per buffer, issued
+// by a single thread.  In the cp.async version the per-thread address arithmetic of staging a (64+32) x 112 window
+// every 32 keys was ~40 % of all executed instructions.
+//   smem: Q 8 KB | K[2] 8 KB | V[2] 8 KB | A-window[2] 64 x 224 B | B-window[2] 32 x 224 B | barriers  (~67 KB, 3 CTAs/SM)
+// =================================================================================================
+constexpr int kRelRowB = kRelBW * 2;        // dense TMA box row: 112 bf16 = 224 bytes
+
+__global__ void __launch_bounds__(128)
+deberta_attn_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                            const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmA,
+                            const __grid_constant__ CUtensorMap tmB, AttnParams p) {
+  constexpr int D = 64, BM = 64, BN = 32, KS = D / 16, NT = BN / 8;
+  constexpr int kQ = 0, kK = BM * D * 2, kV = kK + 2 * BN * D * 2, kA = kV + 2 * BN * D * 2,
+                kB = kA + 2 * BM * kRelRowB, kBar = kB + 2 * BN * kRelRowB;
+  constexpr uint32_t kBlockTx = 2 * BN * D * 2 + (BM + BN) * kRelRowB;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + kBar);      // [0] Q, [1..2] per-buffer block data
+
+  int seq, m_blk, seq_start, seq_len;
+  if (!locate_block<BM>(p.cu_seqlens, p.num_seqs, blockIdx.x, seq, m_blk, seq_start, seq_len)) return;
+  const int head = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
+  const int q0 = m_blk * BM;
+  const int n_blocks = (seq_len + BN - 1) / BN;
+  const int tab_row0 = head * p.total_tokens + seq_start;           // row of this sequence in the [H*T, NB] tables
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_init(&bar[2], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  auto issue_block = [&](int nb, int buf) {                         // thread 0 only
+    const int key0 = nb * BN;
+    const int c_lo = rel_window_lo(p, q0, key0, BN);
+    uint64_t* b = &bar[1 + buf];
+    mbar_arrive_expect_tx(b, kBlockTx);
+    tma_load_2d(smem + kK + buf * BN * D * 2, &tmK, b, head * D, seq_start + key0);
+    tma_load_2d(smem + kV + buf * BN * D * 2, &tmV, b, head * D, seq_start + key0);
+    tma_load_2d(smem + kA + buf * BM * kRelRowB, &tmA, b, c_lo, tab_row0 + q0);
+    tma_load_2d(smem + kB + buf * BN * kRelRowB, &tmB, b, c_lo, tab_row0 + key0);
+  };
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(&bar[0], BM * D * 2);
+    tma_load_2d(smem + kQ, &tmQ, &bar[0], head * D, seq_start + q0);
+    issue_block(0, 0);
+  }
+
+  float o[D / 8][4];
+#pragma unroll
+  for (int i = 0; i < D / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+  float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+  uint32_t qf[KS][4];
+  const int row_a = q0 + warp * 16 + g, row_b = row_a + 8;
+  const short* lut = p.bucket_lut + p.lut_center;
+
+  mbar_wait(&bar[0], 0);
+  {
+    const uint32_t qb = smem_u32(smem + kQ);
+    const int mrow = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, mcol = lane >> 4;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) ldsm_x4(qf[ks], qb + tile_off<D>(mrow, ks * 2 + mcol));
+  }
+
+  for (int nb = 0; nb < n_blocks; ++nb) {
+    const int buf = nb & 1;
+    // buffer buf^1 was last read in iteration nb-1, which ended with __syncthreads()
+    if (threadIdx.x == 0 && nb + 1 < n_blocks) issue_block(nb + 1, buf ^ 1);
+    mbar_wait(&bar[1 + buf], (nb >> 1) & 1);
+    const uint32_t kb = smem_u32(smem + kK + buf * BN * D * 2), vb = smem_u32(smem + kV + buf * BN * D * 2);
+
+    float s[NT][4];
+#pragma unroll
+    for (int i = 0; i < NT; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+      for (int np = 0; np < NT / 2; ++np) {
+        uint32_t kf[4];
+        const int mrow = np * 16 + (lane & 7) + (lane >> 4) * 8, mcol = (lane >> 3) & 1;
+        ldsm_x4(kf, kb + tile_off<D>(mrow, ks * 2 + mcol));
+        mma16816(s[np * 2], qf[ks], kf[0], kf[1]);
+        mma16816(s[np * 2 + 1], qf[ks], kf[2], kf[3]);
+      }
+    }
+    // ---- bias: A[i, c(i-j)] + B[j, c(i-j)] from the two windows ----
+    const int key0 = nb * BN;
+    {
+      const int c_lo_cur = rel_window_lo(p, q0, key0, BN);
+      const int dmin = max(q0 - (key0 + BN - 1), -p.lut_center), dmax = min(q0 + BM - 1 - key0, p.lut_center);
+      const int c_min = lut[dmin], c_max = lut[dmax];
+      const uint32_t sa_a = smem_u32(smem + kA + buf * BM * kRelRowB) + static_cast<uint32_t>(row_a - q0) * kRelRowB;
+      const uint32_t sa_b = sa_a + 8 * kRelRowB;
+      const uint32_t sb0 = smem_u32(smem + kB + buf * BN * kRelRowB) + static_cast<uint32_t>(t4 * 2) * kRelRowB;
+      if (c_min == c_max) {
+        // far-from-diagonal tile: one bucket for every (i, j) -> bias = A[i, c0] + B[j, c0] (rank-1, no lookups)
+        const uint32_t cw = static_cast<uint32_t>(c_min - c_lo_cur) * 2u;
+        const float a0 = lds_bf16(sa_a + cw), a1 = lds_bf16(sa_b + cw);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          const float b0 = lds_bf16(sb0 + (nt * 8) * kRelRowB + cw), b1 = lds_bf16(sb0 + (nt * 8 + 1) * kRelRowB + cw);
+          s[nt][0] += a0 + b0; s[nt][1] += a0 + b1; s[nt][2] += a1 + b0; s[nt][3] += a1 + b1;
+        }
+      } else {
+        // general tile (see flash_fwd_kernel): row_a + 8 reuses row_a's bucket indices one key group later
+        const short* lut_row = lut + (row_a - key0 - t4 * 2);
+        uint32_t cw2[NT + 1][2];
+#pragma unroll
+        for (int g8 = 0; g8 <= NT; ++g8)
+#pragma unroll
+          for (int e1 = 0; e1 < 2; ++e1) {
+            const int c = lut_row[-((g8 - 1) * 8 + e1)];
+            cw2[g8][e1] = min(static_cast<uint32_t>(c - c_lo_cur), static_cast<uint32_t>(kRelBW - 1)) * 2u;
+          }
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+          for (int e1 = 0; e1 < 2; ++e1) {
+            const uint32_t brow = sb0 + (nt * 8 + e1) * kRelRowB;
+            const uint32_t wa = cw2[nt + 1][e1], wb = cw2[nt][e1];
+            s[nt][e1] += lds_bf16(sa_a + wa) + lds_bf16(brow + wa);
+            s[nt][2 + e1] += lds_bf16(sa_b + wb) + lds_bf16(brow + wb);
+          }
+      }
+    }
+    if (key0 + BN > seq_len) {
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (key0 + nt * 8 + t4 * 2 + (e & 1) >= seq_len) s[nt][e] = -INFINITY;
+    }
+    // ---- online softmax (unscaled scores, the scale rides in the exp2 FMA) ----
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      mx[0] = fmaxf(mx[0], fmaxf(s[nt][0], s[nt][1]));
+      mx[1] = fmaxf(mx[1], fmaxf(s[nt][2], s[nt][3]));
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+    }
+    float corr[2], ps[2] = {0.f, 0.f};
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const float mn = fmaxf(m_run[r], mx[r] * p.scale_log2);      // key 0 is always live: finite from block 0 on
+      corr[r] = exp2f(m_run[r] - mn);
+      m_run[r] = mn;
+    }
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float pv = exp2f(fmaf(s[nt][e], p.scale_log2, -m_run[e >> 1]));
+        s[nt][e] = pv;
+        ps[e >> 1] += pv;
+      }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      ps[r] += __shfl_xor_sync(0xffffffffu, ps[r], 1);
+      ps[r] += __shfl_xor_sync(0xffffffffu, ps[r], 2);
+      l_run[r] = l_run[r] * corr[r] + ps[r];
+    }
+#pragma unroll
+    for (int i = 0; i < D / 8; ++i) {
+      o[i][0] *= corr[0]; o[i][1] *= corr[0]; o[i][2] *= corr[1]; o[i][3] *= corr[1];
+    }
+    // ---- O += P V ----
+#pragma unroll
+    for (int ks = 0; ks < BN / 16; ++ks) {
+      uint32_t pa[4];
+      pa[0] = pack_bf16x2(s[2 * ks][0], s[2 * ks][1]);
+      pa[1] = pack_bf16x2(s[2 * ks][2], s[2 * ks][3]);
+      pa[2] = pack_bf16x2(s[2 * ks + 1][0], s[2 * ks + 1][1]);
+      pa[3] = pack_bf16x2(s[2 * ks + 1][2], s[2 * ks + 1][3]);
+#pragma unroll
+      for (int nd = 0; nd < D / 16; ++nd) {
+        uint32_t vf[4];
+        const int mrow = ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, mcol = lane >> 4;
+        ldsm_x4_t(vf, vb + tile_off<D>(mrow, nd * 2 + mcol));
+        mma16816(o[nd * 2], pa, vf[0], vf[1]);
+        mma16816(o[nd * 2 + 1], pa, vf[2], vf[3]);
+      }
+    }
+    __syncthreads();
+  }
+
   const float inv_a = l_run[0] > 0.f ? 1.f / l_run[0] : 0.f, inv_b = l_run[1] > 0.f ? 1.f / l_run[1] : 0.f;
   __nv_bfloat16* obase = p.out + static_cast<long>(seq_start) * p.o_stride_t + head * D;
 #pragma unroll
@@ -867,5 +1099,24 @@ extern "C" cudaError_t nrl_attn_varlen_bwd(const void* dout, const void* q, cons
     flash_bwd_dkdv_kernel<64><<<grid_kv, 128, smem_kv, s>>>(p);
     flash_bwd_dq_kernel<64><<<grid_q, 128, smem_q, s>>>(p);
   }
+  return cudaGetLastError();
+}
+
+// TMA-fed DeBERTa attention: maps = {Q [T,H*64] box 64x64 sw128, K box 32 rows, V box 32 rows, relA [H*T,NB] box 64 x 112
+// (no swizzle), relB box 32 x 112}
+extern "C" cudaError_t nrl_deberta_attn_fwd(const CUtensorMap* maps, void* out, float* lse, long os, const int* cu, int num_seqs,
+                                            int total, int Hq, float scale, const short* lut, int lut_center, int NB,
+                                            cudaStream_t s) {
+  using namespace nrl;
+  if (total == 0) return cudaSuccess;
+  AttnParams p = make_params(nullptr, nullptr, nullptr, 0, 0, 0, os, cu, num_seqs, total, Hq, Hq, scale);
+  p.out = static_cast<__nv_bfloat16*>(out);
+  p.lse = lse;
+  p.bucket_lut = lut; p.lut_center = lut_center; p.NB = NB;
+  constexpr int smem = 64 * 64 * 2 + 4 * 32 * 64 * 2 + 2 * (64 + 32) * kRelRowB + 64;
+  cudaError_t e;
+  if ((e = set_smem(deberta_attn_fwd_tma_kernel, smem)) != cudaSuccess) return e;
+  dim3 grid(total / 64 + num_seqs, Hq);
+  deberta_attn_fwd_tma_kernel<<<grid, 128, smem, s>>>(maps[0], maps[1], maps[2], maps[3], maps[4], p);
   return cudaGetLastError();
 }

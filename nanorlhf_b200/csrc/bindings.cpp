@@ -469,7 +469,7 @@ std::tuple<torch::Tensor, torch::Tensor> attn_varlen_fwd(const torch::Tensor& q,
     lp = reinterpret_cast<const short*>(lut->data_ptr());
     center = (lut->numel() - 1) / 2;
     NB = rel_a->size(2);
-    TORCH_CHECK(center >= max_seqlen - 1, "bucket LUT is too short for max_seqlen");
+    TORCH_CHECK(center >= max_seqlen + 63, "bucket LUT is too short for max_seqlen (needs a 64-entry margin)");
     TORCH_CHECK(NB % 8 == 0);
   }
   check(nrl_attn_varlen_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr<float>(), q.stride(0),
@@ -477,6 +477,34 @@ std::tuple<torch::Tensor, torch::Tensor> attn_varlen_fwd(const torch::Tensor& q,
                             Hkv, D, static_cast<float>(scale), causal ? 1 : 0, ra, rb, lp, center, NB, cur_stream()),
         "attn_varlen_fwd");
   return {out, lse};
+}
+
+// DeBERTa disentangled attention (non-causal, D = 64), every tile TMA-fed.  rel_a / rel_b: [H, T, NB] bf16.
+torch::Tensor deberta_attn_fwd(const torch::Tensor& q, const torch::Tensor& k, const torch::Tensor& v,
+                               const torch::Tensor& cu_seqlens, int64_t max_seqlen, double scale, const torch::Tensor& rel_a,
+                               const torch::Tensor& rel_b, const torch::Tensor& lut) {
+  check_thd(q, "q"); check_thd(k, "k"); check_thd(v, "v");
+  TORCH_CHECK(cu_seqlens.scalar_type() == torch::kInt32 && cu_seqlens.is_contiguous());
+  TORCH_CHECK(rel_a.is_contiguous() && rel_b.is_contiguous() && rel_a.scalar_type() == torch::kBFloat16 &&
+              rel_b.scalar_type() == torch::kBFloat16 && rel_a.sizes() == rel_b.sizes() && rel_a.dim() == 3);
+  TORCH_CHECK(lut.scalar_type() == torch::kInt16 && lut.is_contiguous());
+  c10::cuda::CUDAGuard guard(q.device());
+  const int T = q.size(0), H = q.size(1), D = q.size(2), NB = rel_a.size(2);
+  TORCH_CHECK(D == 64 && k.size(1) == H && rel_a.size(0) == H && rel_a.size(1) == T && NB % 8 == 0);
+  const int center = (lut.numel() - 1) / 2;
+  TORCH_CHECK(center >= max_seqlen + 63, "bucket LUT is too short for max_seqlen (needs a 64-entry margin)");
+  torch::Tensor out = torch::empty({T, H, D}, q.options());
+  auto bf = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const CUtensorMap maps[5] = {
+      nrl::make_tma_2d(q.data_ptr(), T, static_cast<uint64_t>(H) * D, q.stride(0) * 2, 64, 64, bf, 2),
+      nrl::make_tma_2d(k.data_ptr(), T, static_cast<uint64_t>(H) * D, k.stride(0) * 2, 32, 64, bf, 2),
+      nrl::make_tma_2d(v.data_ptr(), T, static_cast<uint64_t>(H) * D, v.stride(0) * 2, 32, 64, bf, 2),
+      nrl::make_tma_2d_plain(rel_a.data_ptr(), static_cast<uint64_t>(H) * T, NB, static_cast<uint64_t>(NB) * 2, 64, 112, bf, 2),
+      nrl::make_tma_2d_plain(rel_b.data_ptr(), static_cast<uint64_t>(H) * T, NB, static_cast<uint64_t>(NB) * 2, 32, 112, bf, 2)};
+  check(nrl_deberta_attn_fwd(maps, out.data_ptr(), nullptr, out.stride(0), cu_seqlens.data_ptr<int>(), cu_seqlens.numel() - 1, T,
+                             H, static_cast<float>(scale), reinterpret_cast<const short*>(lut.data_ptr()), center, NB,
+                             cur_stream()), "deberta_attn_fwd");
+  return out;
 }
 
 // tcgen05 forward: causal, D = 128, bf16.  q/k/v may be strided views (row stride multiple of 8 elements).
@@ -666,6 +694,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("lut") = py::none());
   m.def("attn_varlen_bwd", &attn_varlen_bwd);
   m.def("attn_bwd_tc", &attn_bwd_tc);
+  m.def("deberta_attn_fwd", &deberta_attn_fwd);
   m.def("attn_fwd_tc", &attn_fwd_tc, py::arg("q"), py::arg("k"), py::arg("v"), py::arg("cu_seqlens"), py::arg("scale"),
         py::arg("prof") = py::none());
   m.def("kv_cache_write_fp8", &kv_cache_write_fp8, py::arg("k"), py::arg("v"), py::arg("kq"), py::arg("vq"), py::arg("ks"), py::arg("vs"),

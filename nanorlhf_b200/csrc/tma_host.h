@@ -44,4 +44,25 @@ inline CUtensorMap make_tma_2d(const void* base, uint64_t rows, uint64_t cols, u
   return m;
 }
 
+// Same, without swizzle: the box lands densely in shared memory (box_cols * elem_bytes per row, a multiple of 16).
+inline CUtensorMap make_tma_2d_plain(const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_bytes,
+                                     uint32_t box_rows, uint32_t box_cols, CUtensorMapDataType dtype, int elem_bytes) {
+  thread_local bool ctx_bound = (cudaFree(nullptr) == cudaSuccess);
+  (void)ctx_bound;
+  CUtensorMap m;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {row_stride_bytes};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  if ((box_cols * elem_bytes) % 16 != 0 || box_cols > 256 || box_rows > 256)
+    throw std::runtime_error("TMA box: inner extent must be a multiple of 16 bytes, extents <= 256");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (row_stride_bytes & 15))
+    throw std::runtime_error("TMA tensors need 16-byte aligned base and row stride");
+  CUresult r = tensor_map_encoder()(&m, dtype, 2, const_cast<void*>(base), dims, strides, box, estr,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled failed: " + std::to_string(int(r)));
+  return m;
+}
+
 }  // namespace nrl

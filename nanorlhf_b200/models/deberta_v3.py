@@ -130,12 +130,18 @@ class DisentangledSelfAttention(nn.Module):
         rel_b = torch.bmm(k.transpose(0, 1), pos_q.transpose(1, 2)).contiguous()
         scale = 1.0 / math.sqrt(self.dh * self.scale_factor)
         native._count()
-        out, _ = native.ext().attn_varlen_fwd(q, k, v, cu_seqlens, int(max_len), scale, False, rel_a, rel_b, lut)
+        if os.environ.get("NANORLHF_DEBERTA_TMA", "1") != "0" and self.dh == 64:
+            # every tile (Q, K, V and the two sliding bias-table windows) arrives by TMA
+            out = native.ext().deberta_attn_fwd(q, k, v, cu_seqlens, int(max_len), scale, rel_a, rel_b, lut)
+        else:
+            out, _ = native.ext().attn_varlen_fwd(q, k, v, cu_seqlens, int(max_len), scale, False, rel_a, rel_b, lut)
         return out.reshape(T, -1)
 
 
 def build_bucket_lut(max_len: int, bucket_size: int, max_position: int, span: int, device) -> torch.Tensor:
-    """int16 table: delta in [-max_len, max_len] -> clamp(bucket(delta) + span, 0, 2*span-1)."""
+    """int16 table: delta -> clamp(bucket(delta) + span, 0, 2*span-1) for |delta| <= max_len + 64.  The margin
+    covers the padded tail rows / keys of the last attention tiles, so the kernel indexes it without clamping."""
+    max_len = max_len + 64
     d = torch.arange(-max_len, max_len + 1, device=device)
     b = make_log_bucket_position(d, bucket_size, max_position) if (bucket_size > 0 and max_position > 0) else d
     return (b + span).clamp(0, 2 * span - 1).to(torch.int16).contiguous()
