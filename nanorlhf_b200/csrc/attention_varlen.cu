@@ -347,13 +347,14 @@ __global__ void __launch_bounds__(128) flash_fwd_kernel(AttnParams p) {
 // every 32 keys was ~40 % of all executed instructions.
 //   smem: Q 8 KB | K[2] 8 KB | V[2] 8 KB | A-window[2] 64 x 224 B | B-window[2] 32 x 224 B | barriers  (~67 KB, 3 CTAs/SM)
 // =================================================================================================
-constexpr int kRelRowB = kRelBW * 2;        // dense TMA box row: 112 bf16 = 224 bytes
-
+template <int BN>
 __global__ void __launch_bounds__(128)
 deberta_attn_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                             const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmA,
                             const __grid_constant__ CUtensorMap tmB, AttnParams p) {
-  constexpr int D = 64, BM = 64, BN = 32, KS = D / 16, NT = BN / 8;
+  constexpr int D = 64, BM = 64, KS = D / 16, NT = BN / 8;
+  constexpr int kW = (BN == 32) ? 112 : 136;      // window columns: >= 64 + BN - 1 + 7, multiple of 8
+  constexpr int kRelRowB = kW * 2;               // dense TMA box row (bytes)
   constexpr int kQ = 0, kK = BM * D * 2, kV = kK + 2 * BN * D * 2, kA = kV + 2 * BN * D * 2,
                 kB = kA + 2 * BM * kRelRowB, kBar = kB + 2 * BN * kRelRowB;
   constexpr uint32_t kBlockTx = 2 * BN * D * 2 + (BM + BN) * kRelRowB;
@@ -453,7 +454,7 @@ deberta_attn_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
 #pragma unroll
           for (int e1 = 0; e1 < 2; ++e1) {
             const int c = lut_row[-((g8 - 1) * 8 + e1)];
-            cw2[g8][e1] = min(static_cast<uint32_t>(c - c_lo_cur), static_cast<uint32_t>(kRelBW - 1)) * 2u;
+            cw2[g8][e1] = min(static_cast<uint32_t>(c - c_lo_cur), static_cast<uint32_t>(kW - 1)) * 2u;
           }
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt)
@@ -1105,7 +1106,7 @@ extern "C" cudaError_t nrl_attn_varlen_bwd(const void* dout, const void* q, cons
 // TMA-fed DeBERTa attention: maps = {Q [T,H*64] box 64x64 sw128, K box 32 rows, V box 32 rows, relA [H*T,NB] box 64 x 112
 // (no swizzle), relB box 32 x 112}
 extern "C" cudaError_t nrl_deberta_attn_fwd(const CUtensorMap* maps, void* out, float* lse, long os, const int* cu, int num_seqs,
-                                            int total, int Hq, float scale, const short* lut, int lut_center, int NB,
+                                            int total, int Hq, float scale, const short* lut, int lut_center, int NB, int bn,
                                             cudaStream_t s) {
   using namespace nrl;
   if (total == 0) return cudaSuccess;
@@ -1113,10 +1114,16 @@ extern "C" cudaError_t nrl_deberta_attn_fwd(const CUtensorMap* maps, void* out, 
   p.out = static_cast<__nv_bfloat16*>(out);
   p.lse = lse;
   p.bucket_lut = lut; p.lut_center = lut_center; p.NB = NB;
-  constexpr int smem = 64 * 64 * 2 + 4 * 32 * 64 * 2 + 2 * (64 + 32) * kRelRowB + 64;
   cudaError_t e;
-  if ((e = set_smem(deberta_attn_fwd_tma_kernel, smem)) != cudaSuccess) return e;
   dim3 grid(total / 64 + num_seqs, Hq);
-  deberta_attn_fwd_tma_kernel<<<grid, 128, smem, s>>>(maps[0], maps[1], maps[2], maps[3], maps[4], p);
+  if (bn == 64) {
+    constexpr int smem = 64 * 64 * 2 + 4 * 64 * 64 * 2 + 2 * (64 + 64) * 136 * 2 + 64;
+    if ((e = set_smem(deberta_attn_fwd_tma_kernel<64>, smem)) != cudaSuccess) return e;
+    deberta_attn_fwd_tma_kernel<64><<<grid, 128, smem, s>>>(maps[0], maps[1], maps[2], maps[3], maps[4], p);
+  } else {
+    constexpr int smem = 64 * 64 * 2 + 4 * 32 * 64 * 2 + 2 * (64 + 32) * 112 * 2 + 64;
+    if ((e = set_smem(deberta_attn_fwd_tma_kernel<32>, smem)) != cudaSuccess) return e;
+    deberta_attn_fwd_tma_kernel<32><<<grid, 128, smem, s>>>(maps[0], maps[1], maps[2], maps[3], maps[4], p);
+  }
   return cudaGetLastError();
 }

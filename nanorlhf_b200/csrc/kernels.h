@@ -72,7 +72,7 @@ cudaError_t nrl_attn_fwd_tc(const CUtensorMap* tmQ, const CUtensorMap* tmK, cons
                             cudaStream_t s, long long* prof = nullptr);
 // TMA-fed DeBERTa disentangled attention (attention_varlen.cu); maps = {Q, K, V, relA, relB}
 cudaError_t nrl_deberta_attn_fwd(const CUtensorMap* maps, void* out, float* lse, long os, const int* cu, int num_seqs,
-                                 int total, int Hq, float scale, const short* lut, int lut_center, int NB, cudaStream_t s);
+                                 int total, int Hq, float scale, const short* lut, int lut_center, int NB, int bn, cudaStream_t s);
 // tcgen05 backward (attention_bwd_tc.cu): delta + dK/dV + dQ; `maps` = 8 tensor maps (see the .cu)
 cudaError_t nrl_attn_bwd_tc(const CUtensorMap* maps, const void* o, const void* dout, const float* lse, float* delta,
                             void* dq, void* dk, void* dv, long o_stride_t, long dq_stride_t, long dkv_stride_t,
