@@ -57,7 +57,7 @@ int pick_block_n(int64_t M, int64_t N, bool allow_192 = false) {
 
 // D[M,N] = A[M,K] @ B[N,K]^T (+ bias[N])
 torch::Tensor gemm_bf16(const torch::Tensor& a, const torch::Tensor& b, const c10::optional<torch::Tensor>& bias,
-                        c10::optional<torch::Tensor> out_opt, int64_t block_n) {
+                        c10::optional<torch::Tensor> out_opt, int64_t block_n, int64_t act) {
   check_bf16_2d(a, "a");
   check_bf16_2d(b, "b");
   const int64_t M = a.size(0), K = a.size(1), N = b.size(0);
@@ -74,6 +74,7 @@ torch::Tensor gemm_bf16(const torch::Tensor& a, const torch::Tensor& b, const c1
   CUtensorMap tmD = nrl::make_tma_2d(out.data_ptr(), M, N, out.stride(0) * 2, 128, 64, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2);
   nrl::GemmParams p{};
   p.M = M; p.N = N; p.K = K; p.n_splits = 1; p.scale = 1.f;
+  p.act = static_cast<int>(act);
   if (bias.has_value()) {
     TORCH_CHECK(bias->is_cuda() && bias->scalar_type() == torch::kBFloat16 && bias->numel() == N && bias->is_contiguous(),
                 "bias must be a contiguous CUDA bf16 [N] tensor");
@@ -510,6 +511,25 @@ torch::Tensor deberta_attn_fwd(const torch::Tensor& q, const torch::Tensor& k, c
   return out;
 }
 
+// y = LayerNorm(x + residual) (residual optional); bf16 [rows, d], d <= 2048
+torch::Tensor add_layernorm(const torch::Tensor& x, const c10::optional<torch::Tensor>& residual, const torch::Tensor& w,
+                            const torch::Tensor& b, double eps) {
+  check_bf16_2d(x, "x");
+  TORCH_CHECK(x.is_contiguous() && w.is_contiguous() && b.is_contiguous() && w.scalar_type() == torch::kBFloat16 &&
+              b.scalar_type() == torch::kBFloat16 && w.numel() == x.size(1) && b.numel() == x.size(1));
+  const void* rp = nullptr;
+  if (residual.has_value()) {
+    check_bf16_2d(*residual, "residual");
+    TORCH_CHECK(residual->is_contiguous() && residual->sizes() == x.sizes());
+    rp = residual->data_ptr();
+  }
+  c10::cuda::CUDAGuard guard(x.device());
+  torch::Tensor y = torch::empty_like(x);
+  check(nrl_add_layernorm(x.data_ptr(), rp, w.data_ptr(), b.data_ptr(), y.data_ptr(), x.size(0), x.size(1),
+                          static_cast<float>(eps), cur_stream()), "add_layernorm");
+  return y;
+}
+
 // tcgen05 forward: causal, D = 128, bf16.  q/k/v may be strided views (row stride multiple of 8 elements).
 std::tuple<torch::Tensor, torch::Tensor> attn_fwd_tc(const torch::Tensor& q, const torch::Tensor& k, const torch::Tensor& v,
                                                      const torch::Tensor& cu_seqlens, double scale,
@@ -665,7 +685,8 @@ torch::Tensor paged_decode_fp8(const torch::Tensor& q, const torch::Tensor& kq, 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "nanorlhf_b200 sm_100a kernels";
   m.def("gemm_bf16", &gemm_bf16, py::arg("a"), py::arg("b"), py::arg("bias") = py::none(), py::arg("out") = py::none(),
-        py::arg("block_n") = 0);
+        py::arg("block_n") = 0, py::arg("act") = 0);
+  m.def("add_layernorm", &add_layernorm);
   m.def("lmhead_logprob_fwd", &lmhead_logprob_fwd, py::arg("hidden"), py::arg("weight"), py::arg("targets"),
         py::arg("inv_temperature"), py::arg("n_splits") = 0);
   m.def("lmhead_dlogits", &lmhead_dlogits);

@@ -246,6 +246,87 @@ extern "C" cudaError_t nrl_rmsnorm(const void* x, const void* residual, const vo
   return cudaGetLastError();
 }
 
+// y = LayerNorm(x + residual) * w + b  (inference path of the reward model: the add and the norm in one pass).
+// One warp per row, d <= 2048, row cached in registers, two-pass (mean, then centred variance) in fp32.
+__global__ void __launch_bounds__(256) add_layernorm_kernel(const __nv_bfloat16* __restrict__ x,
+                                                            const __nv_bfloat16* __restrict__ residual,
+                                                            const __nv_bfloat16* __restrict__ w,
+                                                            const __nv_bfloat16* __restrict__ b,
+                                                            __nv_bfloat16* __restrict__ y, int rows, int d, float eps) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31, nvec = d / 8;
+  const uint4* xv = reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * d);
+  const uint4* rv = residual ? reinterpret_cast<const uint4*>(residual + static_cast<size_t>(row) * d) : nullptr;
+  constexpr int kMaxVec = 8;                      // 8 vec * 32 lanes * 8 elems = 2048
+  float vals[kMaxVec][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    const int idx = lane + i * 32;
+    if (idx < nvec) {
+      const uint4 a = xv[idx];
+      const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+      uint32_t bw[4] = {0, 0, 0, 0};
+      if (rv != nullptr) {
+        const uint4 r4 = rv[idx];
+        bw[0] = r4.x; bw[1] = r4.y; bw[2] = r4.z; bw[3] = r4.w;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float2 f = unpack_bf16x2(aw[j]);
+        if (rv != nullptr) {
+          const float2 g = unpack_bf16x2(bw[j]);
+          f = unpack_bf16x2(pack_bf16x2(f.x + g.x, f.y + g.y));      // the sum is a bf16 tensor in the eager model
+        }
+        vals[i][2 * j] = f.x;
+        vals[i][2 * j + 1] = f.y;
+        sum += f.x + f.y;
+      }
+    }
+  }
+  const float mean = warp_sum(sum) / d;
+  float var = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i)
+    if (lane + i * 32 < nvec)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float c = vals[i][j] - mean;
+        var += c * c;
+      }
+  const float rstd = rsqrtf(warp_sum(var) / d + eps);
+  const uint4* wv = reinterpret_cast<const uint4*>(w);
+  const uint4* bv = reinterpret_cast<const uint4*>(b);
+  uint4* yv = reinterpret_cast<uint4*>(y + static_cast<size_t>(row) * d);
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    const int idx = lane + i * 32;
+    if (idx < nvec) {
+      const uint4 w4 = wv[idx], b4 = bv[idx];
+      const uint32_t ww[4] = {w4.x, w4.y, w4.z, w4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
+      uint32_t ow[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 wf = unpack_bf16x2(ww[j]), bf = unpack_bf16x2(bb[j]);
+        ow[j] = pack_bf16x2((vals[i][2 * j] - mean) * rstd * wf.x + bf.x, (vals[i][2 * j + 1] - mean) * rstd * wf.y + bf.y);
+      }
+      yv[idx] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    }
+  }
+}
+
+extern "C" cudaError_t nrl_add_layernorm(const void* x, const void* residual, const void* w, const void* b, void* y, int rows,
+                                         int d, float eps, cudaStream_t s) {
+  if (d % 8 != 0 || d > 2048) return cudaErrorInvalidValue;
+  if (rows == 0) return cudaSuccess;
+  add_layernorm_kernel<<<(rows + 7) / 8, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(x),
+                                                     static_cast<const __nv_bfloat16*>(residual),
+                                                     static_cast<const __nv_bfloat16*>(w), static_cast<const __nv_bfloat16*>(b),
+                                                     static_cast<__nv_bfloat16*>(y), rows, d, eps);
+  return cudaGetLastError();
+}
+
 extern "C" cudaError_t nrl_rmsnorm_bwd(const void* x, const void* w, const void* gy, const float* rstd, void* gx,
                                        int rows, int d, cudaStream_t s) {
   if (d % 8 != 0 || d > 8192) return cudaErrorInvalidValue;

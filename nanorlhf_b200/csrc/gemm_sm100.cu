@@ -31,6 +31,19 @@ constexpr int kNumEpiThreads = 128;
 constexpr int kStagingBytes = BLOCK_M * 128;   // 128 rows x 64 bf16
 constexpr int GROUP_M = 16;
 
+// GELU(x) = x/2 * (1 + erf(x / sqrt 2)) with erf from Abramowitz-Stegun 7.1.26 (|error| < 1.5e-7): two MUFU ops and
+// seven FMAs, cheap enough to hide under the next tile's MMAs (libdevice erff made the epilogue the bottleneck).
+NRL_DEVICE float gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float erf_abs = 1.f - poly * t * exp2f(-z * z * 1.4426950408889634f);
+  return 0.5f * x * (1.f + copysignf(erf_abs, x));
+}
+
 template <int BLOCK_N>
 struct SmemLayout {
   static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
@@ -345,6 +358,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                   if (p.bias != nullptr) {
                     if (col < p.N) x0 += __bfloat162float(p.bias[col]);
                     if (col + 1 < p.N) x1 += __bfloat162float(p.bias[col + 1]);
+                  }
+                  if (p.act == 1) {           // exact-form GELU on the fp32 accumulator
+                    x0 = gelu_erf(x0);
+                    x1 = gelu_erf(x1);
                   }
                 } else {  // EPI_DLOGITS
                   float p0 = exp2f((x0 * p.scale - row_lse) * kLog2e);

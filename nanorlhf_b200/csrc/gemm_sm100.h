@@ -27,6 +27,7 @@ struct GemmParams {
   const float* col_scale;       // fp8 GEMM: [N] per-output-channel dequant scale of B
   const __nv_bfloat16* addend;  // EPI_MERGE: [M, N] row-major, row stride addend_stride elements
   long addend_stride;
+  int act;                      // EPI_STORE: 0 = none, 1 = exact (erf) GELU applied after the bias
 };
 
 }  // namespace nrl

@@ -14,6 +14,8 @@ struct AdamHyper {
 }  // namespace nrl
 
 extern "C" {
+cudaError_t nrl_add_layernorm(const void* x, const void* residual, const void* w, const void* b, void* y, int rows, int d,
+                              float eps, cudaStream_t s);
 cudaError_t nrl_rmsnorm(const void* x, const void* residual, const void* w, void* y, void* residual_out, float* rstd,
                         int rows, int d, float eps, cudaStream_t s);
 cudaError_t nrl_rmsnorm_bwd(const void* x, const void* w, const void* gy, const float* rstd, void* gx, int rows, int d,

@@ -43,10 +43,16 @@ def launches() -> int:
 # --------------------------------------------------------------------------------------------
 # GEMM
 # --------------------------------------------------------------------------------------------
-def gemm_bf16(a, b, bias=None, out=None, block_n: int = 0):
+def add_layernorm(x, residual, weight, bias, eps):
+    """LayerNorm(x + residual) in one pass (inference; reward model)."""
+    _count()
+    return ext().add_layernorm(x, residual, weight, bias, float(eps))
+
+
+def gemm_bf16(a, b, bias=None, out=None, block_n: int = 0, act: int = 0):
     """a[M,K] @ b[N,K]^T (+bias) on the tcgen05 kernel; inputs must be bf16, K-contiguous."""
     _count()
-    return ext().gemm_bf16(a, b, bias, out, block_n)
+    return ext().gemm_bf16(a, b, bias, out, block_n, act)
 
 
 class _LinearFn(torch.autograd.Function):

@@ -291,6 +291,25 @@ def test_attention_bwd_tcgen05(Hq, Hkv, lens):
         assert _rel(a, b) < 3e-2, (name, _rel(a, b))
 
 
+def test_gemm_gelu_epilogue_and_add_layernorm():
+    n = _native()
+    torch.manual_seed(0)
+    x = torch.randn(1000, 1024, device="cuda").bfloat16()
+    w = (torch.randn(4096, 1024, device="cuda") * 0.03).bfloat16()
+    b = torch.randn(4096, device="cuda").bfloat16()
+    y = n.gemm_bf16(x, w, b, act=1)
+    want = torch.nn.functional.gelu(x.float() @ w.float().t() + b.float())
+    assert _rel(y, want) < 1e-2
+    r = torch.randn(1000, 1024, device="cuda").bfloat16()
+    lw, lb = torch.randn(1024, device="cuda").bfloat16(), torch.randn(1024, device="cuda").bfloat16()
+    z = n.add_layernorm(x, r, lw, lb, 1e-7)
+    want = torch.nn.functional.layer_norm((x + r).float(), (1024,), lw.float(), lb.float(), 1e-7)
+    assert _rel(z, want) < 1e-2
+    z2 = n.add_layernorm(x[:, :200].contiguous(), None, lw[:200].contiguous(), lb[:200].contiguous(), 1e-5)
+    want2 = torch.nn.functional.layer_norm(x[:, :200].float(), (200,), lw[:200].float(), lb[:200].float(), 1e-5)
+    assert _rel(z2, want2) < 1e-2
+
+
 def test_deberta_tma_attention_matches_cp_async_kernel():
     """TMA-fed disentangled attention vs the cp.async kernel (same math) and vs a dense fp32 oracle."""
     from nanorlhf_b200.models.deberta_v3 import build_bucket_lut
@@ -332,7 +351,8 @@ def test_deberta_fused_attention_matches_eager():
     ids[0, 650:] = 0
     ids[2, 33:] = 0
     ids[4, 1:] = 0
-    fused = m(ids)
+    with torch.no_grad():                                  # no-grad: GEMM+GELU epilogue and add+LayerNorm kernels too
+        fused = m(ids)
     os.environ["NANORLHF_DEBERTA"] = "eager"
     try:
         eager = m(ids)
