@@ -111,7 +111,7 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   uint64_t* pds_free = pds_ready + 2;          // [wg]  the dV / dK MMAs that read them retired
   uint64_t* done_bar = pds_free + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(done_bar + 1);
-  int* info = reinterpret_cast<int*>(tmem_ptr + 1);
+  int* info = reinterpret_cast<int*>(tmem_ptr + 4);      // its own 16-byte slot: tcgen05.alloc writes next to it
 
   int kb, seq_start, seq_len;
   if (!bwd_locate<128>(p.cu_seqlens, p.num_seqs, blockIdx.x, info, kb, seq_start, seq_len)) return;
@@ -338,7 +338,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   uint64_t* ds_free = ds_ready + 2;            // [wg]
   uint64_t* done_bar = ds_free + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(done_bar + 1);
-  int* info = reinterpret_cast<int*>(tmem_ptr + 1);
+  int* info = reinterpret_cast<int*>(tmem_ptr + 4);      // its own 16-byte slot: tcgen05.alloc writes next to it
 
   int mb, seq_start, seq_len;
   // latest (longest) query blocks first
