@@ -68,6 +68,23 @@ torch::Tensor gemm_bf16(const torch::Tensor& a, const torch::Tensor& b, const c1
   check_bf16_2d(out, "out");
   TORCH_CHECK(out.size(0) == M && out.size(1) == N, "out has the wrong shape");
   if (M == 0) return out;
+  // block_n == 512 selects the experimental 2-CTA kernel (256 x 256 tile per CTA pair); NRL_GEMM_2CTA=1 makes it the
+  // automatic choice for N >= 256.  Not the default until it has been validated on hardware.
+  static const bool auto_2cta = getenv("NRL_GEMM_2CTA") && atoi(getenv("NRL_GEMM_2CTA")) == 1;
+  if (block_n == 512 || (block_n == 0 && auto_2cta && N >= 256 && M >= 256)) {
+    CUtensorMap tmA2 = nrl::make_tma_2d(a.data_ptr(), M, K, a.stride(0) * 2, 128, 64, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2);
+    CUtensorMap tmB2 = nrl::make_tma_2d(b.data_ptr(), N, K, b.stride(0) * 2, 128, 64, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2);
+    CUtensorMap tmD2 = nrl::make_tma_2d(out.data_ptr(), M, N, out.stride(0) * 2, 128, 64, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2);
+    nrl::GemmParams p2{};
+    p2.M = M; p2.N = N; p2.K = K; p2.n_splits = 1; p2.scale = 1.f;
+    p2.act = static_cast<int>(act);
+    if (bias.has_value()) {
+      TORCH_CHECK(bias->is_cuda() && bias->scalar_type() == torch::kBFloat16 && bias->numel() == N && bias->is_contiguous());
+      p2.bias = reinterpret_cast<const __nv_bfloat16*>(bias->data_ptr());
+    }
+    check(nrl_gemm_bf16_tn_2cta(&tmA2, &tmB2, &tmD2, &p2, num_sms(), cur_stream()), "gemm_bf16_2cta");
+    return out;
+  }
   const int bn = block_n > 0 ? static_cast<int>(block_n) : pick_block_n(M, N, /*allow_192=*/true);
   CUtensorMap tmA = nrl::make_tma_2d(a.data_ptr(), M, K, a.stride(0) * 2, 128, 64, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2);
   CUtensorMap tmB = nrl::make_tma_2d(b.data_ptr(), N, K, b.stride(0) * 2, bn, 64, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2);

@@ -34,6 +34,19 @@ def test_gemm_bf16(M, N, K, bn):
     assert _rel(out2, a.float() @ b.float().t()) < 1e-2
 
 
+@pytest.mark.skipif(__import__("os").environ.get("NRL_GEMM_2CTA") != "1",
+                    reason="experimental cta_group::2 GEMM: opt-in until validated on hardware (NRL_GEMM_2CTA=1)")
+@pytest.mark.parametrize("M,N,K", [(256, 256, 64), (2048, 2048, 1536), (2048, 1536, 8960), (300, 520, 200), (6912, 17920, 1536)])
+def test_gemm_bf16_2cta(M, N, K):
+    n = _native()
+    torch.manual_seed(0)
+    a = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
+    b = torch.randn(N, K, device="cuda", dtype=torch.bfloat16)
+    bias = torch.randn(N, device="cuda", dtype=torch.bfloat16)
+    out = n.gemm_bf16(a, b, bias, None, 512)
+    assert _rel(out, a.float() @ b.float().t() + bias.float()) < 1e-2
+
+
 def test_linear_autograd():
     n = _native()
     torch.manual_seed(0)
