@@ -82,7 +82,7 @@ torch::Tensor gemm_bf16(const torch::Tensor& a, const torch::Tensor& b, const c1
       TORCH_CHECK(bias->is_cuda() && bias->scalar_type() == torch::kBFloat16 && bias->numel() == N && bias->is_contiguous());
       p2.bias = reinterpret_cast<const __nv_bfloat16*>(bias->data_ptr());
     }
-    check(nrl_gemm_bf16_tn_2cta(&tmA2, &tmB2, &tmD2, &p2, num_sms(), cur_stream()), "gemm_bf16_2cta");
+    check(nrl_gemm_bf16_tn_2cta(&tmA2, &tmB2, &tmD2, &p2, 0, num_sms(), cur_stream()), "gemm_bf16_2cta");
     return out;
   }
   const int bn = block_n > 0 ? static_cast<int>(block_n) : pick_block_n(M, N, /*allow_192=*/true);
@@ -111,6 +111,16 @@ torch::Tensor gemm_swiglu(const torch::Tensor& a, const torch::Tensor& w_interle
   torch::Tensor out = out_opt.has_value() ? *out_opt : torch::empty({M, N2 / 2}, a.options());
   check_bf16_2d(out, "out");
   if (M == 0) return out;
+  static const bool auto_2cta = getenv("NRL_GEMM_2CTA") && atoi(getenv("NRL_GEMM_2CTA")) == 1;     // experimental
+  if (auto_2cta && M >= 256 && N2 % 256 == 0) {
+    CUtensorMap tA = nrl::make_tma_2d(a.data_ptr(), M, K, a.stride(0) * 2, 128, 64, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2);
+    CUtensorMap tB = nrl::make_tma_2d(w_interleaved.data_ptr(), N2, K, w_interleaved.stride(0) * 2, 128, 64, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2);
+    CUtensorMap tD = nrl::make_tma_2d(out.data_ptr(), M, N2 / 2, out.stride(0) * 2, 128, 64, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2);
+    nrl::GemmParams p2{};
+    p2.M = M; p2.N = N2; p2.K = K; p2.n_splits = 1; p2.scale = 1.f;
+    check(nrl_gemm_bf16_tn_2cta(&tA, &tB, &tD, &p2, 1, num_sms(), cur_stream()), "gemm_swiglu_2cta");
+    return out;
+  }
   const int bn = pick_block_n(M, N2);
   CUtensorMap tmA = nrl::make_tma_2d(a.data_ptr(), M, K, a.stride(0) * 2, 128, 64, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2);
   CUtensorMap tmB = nrl::make_tma_2d(w_interleaved.data_ptr(), N2, K, w_interleaved.stride(0) * 2, bn, 64, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2);

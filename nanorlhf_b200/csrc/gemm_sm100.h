@@ -37,7 +37,7 @@ extern "C" cudaError_t nrl_gemm_bf16_tn(const CUtensorMap* tmA, const CUtensorMa
                                         cudaStream_t stream);
 // experimental 2-CTA (cta_group::2) bf16 GEMM, EPI_STORE only (gemm_sm100_2cta.cu); B map box = 128 rows
 extern "C" cudaError_t nrl_gemm_bf16_tn_2cta(const CUtensorMap* tmA, const CUtensorMap* tmB, const CUtensorMap* tmD,
-                                             const nrl::GemmParams* p, int num_sms, cudaStream_t stream);
+                                             const nrl::GemmParams* p, int swiglu, int num_sms, cudaStream_t stream);
 extern "C" cudaError_t nrl_gemm_fp8_tn(const CUtensorMap* tmA, const CUtensorMap* tmB, const CUtensorMap* tmD,
                                        const nrl::GemmParams* p, int block_n, int epi, int num_sms, cudaStream_t stream);
 extern "C" cudaError_t nrl_lmhead_combine(const float* partials, int M, int n_splits, float* logp, float* entropy,

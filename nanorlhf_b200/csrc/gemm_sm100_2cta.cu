@@ -99,6 +99,9 @@ NRL_DEVICE PairCoord pair_coord(int t, int num_m2, int num_n) {
   return c;
 }
 
+// SWIGLU = true: B rows are interleaved [32 gate | 32 up] per 64-column chunk (parallel/weight_sync.py); the epilogue
+// forms silu(g) * u on the accumulator tile and stores a [M, N/2] activation (same contract as EPI_SWIGLU).
+template <bool SWIGLU>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const __grid_constant__ CUtensorMap tmD, GemmParams p) {
@@ -205,6 +208,8 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_acc = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(quad * 32) << 16);
+      uint32_t sw_packed[32];
+      (void)sw_packed;
 #pragma unroll 1
       for (int ch64 = 0; ch64 < BLOCK_N / 64; ++ch64) {
         uint32_t v[2][32];
@@ -217,35 +222,54 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);     // the accumulator of this CTA is drained
         }
         const int col0 = c.n_blk * BLOCK_N + ch64 * 64;
-        uint8_t* buf = staging + store_buf * kStagingBytes;
-        if (epi_tid == 0) tma_store_wait_read<1>();
-        named_barrier_sync(1, kEpiThreads);
         uint32_t packed[32];
-#pragma unroll
-        for (int h = 0; h < 2; ++h)
+        int store_col = col0;
+        bool do_store = true;
+        if (SWIGLU) {
+          constexpr float kLog2e = 1.4426950408889634f;
 #pragma unroll
           for (int j = 0; j < 32; j += 2) {
-            float x0 = __uint_as_float(v[h][j]), x1 = __uint_as_float(v[h][j + 1]);
-            const int col = col0 + h * 32 + j;
-            if (p.bias != nullptr) {
-              if (col < p.N) x0 += __bfloat162float(p.bias[col]);
-              if (col + 1 < p.N) x1 += __bfloat162float(p.bias[col + 1]);
-            }
-            if (p.act == 1) { x0 = gelu_erf_2(x0); x1 = gelu_erf_2(x1); }
-            packed[h * 16 + j / 2] = pack_bf16x2(x0, x1);
+            const float g0 = __uint_as_float(v[0][j]), g1 = __uint_as_float(v[0][j + 1]);
+            const float u0 = __uint_as_float(v[1][j]), u1 = __uint_as_float(v[1][j + 1]);
+            sw_packed[(ch64 & 1) * 16 + j / 2] =
+                pack_bf16x2(g0 / (1.f + exp2f(-g0 * kLog2e)) * u0, g1 / (1.f + exp2f(-g1 * kLog2e)) * u1);
           }
-        uint8_t* rowp = buf + row_in_tile * 128;
+          do_store = (ch64 & 1) == 1;                               // two 32-feature halves make one 64-wide slab
+          store_col = c.n_blk * (BLOCK_N / 2) + (ch64 >> 1) * 64;
 #pragma unroll
-        for (int q8 = 0; q8 < 8; ++q8)
-          *reinterpret_cast<uint4*>(rowp + ((q8 ^ (row_in_tile & 7)) * 16)) =
-              make_uint4(packed[q8 * 4], packed[q8 * 4 + 1], packed[q8 * 4 + 2], packed[q8 * 4 + 3]);
-        fence_proxy_async_smem();
-        named_barrier_sync(2, kEpiThreads);
-        if (epi_tid == 0) {
-          tma_store_2d(&tmD, buf, col0, m_blk * BLOCK_M);
-          tma_store_commit();
+          for (int j = 0; j < 32; ++j) packed[j] = sw_packed[j];
+        } else {
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              float x0 = __uint_as_float(v[h][j]), x1 = __uint_as_float(v[h][j + 1]);
+              const int col = col0 + h * 32 + j;
+              if (p.bias != nullptr) {
+                if (col < p.N) x0 += __bfloat162float(p.bias[col]);
+                if (col + 1 < p.N) x1 += __bfloat162float(p.bias[col + 1]);
+              }
+              if (p.act == 1) { x0 = gelu_erf_2(x0); x1 = gelu_erf_2(x1); }
+              packed[h * 16 + j / 2] = pack_bf16x2(x0, x1);
+            }
         }
-        store_buf ^= 1;
+        if (do_store) {
+          uint8_t* buf = staging + store_buf * kStagingBytes;
+          if (epi_tid == 0) tma_store_wait_read<1>();
+          named_barrier_sync(1, kEpiThreads);
+          uint8_t* rowp = buf + row_in_tile * 128;
+#pragma unroll
+          for (int q8 = 0; q8 < 8; ++q8)
+            *reinterpret_cast<uint4*>(rowp + ((q8 ^ (row_in_tile & 7)) * 16)) =
+                make_uint4(packed[q8 * 4], packed[q8 * 4 + 1], packed[q8 * 4 + 2], packed[q8 * 4 + 3]);
+          fence_proxy_async_smem();
+          named_barrier_sync(2, kEpiThreads);
+          if (epi_tid == 0) {
+            tma_store_2d(&tmD, buf, store_col, m_blk * BLOCK_M);
+            tma_store_commit();
+          }
+          store_buf ^= 1;
+        }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
@@ -265,11 +289,13 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 
 // maps: A box 128 rows x 64, B box 128 rows x 64 (half of the 256-wide tile), D box 128 rows x 64
 extern "C" cudaError_t nrl_gemm_bf16_tn_2cta(const CUtensorMap* tmA, const CUtensorMap* tmB, const CUtensorMap* tmD,
-                                             const nrl::GemmParams* p, int num_sms, cudaStream_t stream) {
+                                             const nrl::GemmParams* p, int swiglu, int num_sms, cudaStream_t stream) {
   using namespace nrl::two_cta;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_2cta_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(gemm_bf16_tn_2cta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
     if (e != cudaSuccess) return e;
     configured = true;
   }
@@ -277,6 +303,10 @@ extern "C" cudaError_t nrl_gemm_bf16_tn_2cta(const CUtensorMap* tmA, const CUten
   int pairs = num_m2 * num_n;
   if (pairs > num_sms / 2) pairs = num_sms / 2;
   if (pairs < 1) pairs = 1;
-  gemm_bf16_tn_2cta_kernel<<<2 * pairs, kThreads, kSmemTotal, stream>>>(*tmA, *tmB, *tmD, *p);   // __cluster_dims__(2,1,1)
+  // __cluster_dims__(2, 1, 1): consecutive CTAs form the pairs
+  if (swiglu)
+    gemm_bf16_tn_2cta_kernel<true><<<2 * pairs, kThreads, kSmemTotal, stream>>>(*tmA, *tmB, *tmD, *p);
+  else
+    gemm_bf16_tn_2cta_kernel<false><<<2 * pairs, kThreads, kSmemTotal, stream>>>(*tmA, *tmB, *tmD, *p);
   return cudaGetLastError();
 }
