@@ -231,8 +231,9 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           for (int j = 0; j < 32; j += 2) {
             const float g0 = __uint_as_float(v[0][j]), g1 = __uint_as_float(v[0][j + 1]);
             const float u0 = __uint_as_float(v[1][j]), u1 = __uint_as_float(v[1][j + 1]);
-            sw_packed[(ch64 & 1) * 16 + j / 2] =
-                pack_bf16x2(g0 / (1.f + exp2f(-g0 * kLog2e)) * u0, g1 / (1.f + exp2f(-g1 * kLog2e)) * u1);
+            const uint32_t pk = pack_bf16x2(g0 / (1.f + exp2f(-g0 * kLog2e)) * u0, g1 / (1.f + exp2f(-g1 * kLog2e)) * u1);
+            if ((ch64 & 1) == 0) sw_packed[j / 2] = pk;            // static indices: the array stays in registers
+            else sw_packed[16 + j / 2] = pk;
           }
           do_store = (ch64 & 1) == 1;                               // two 32-feature halves make one 64-wide slab
           store_col = c.n_blk * (BLOCK_N / 2) + (ch64 >> 1) * 64;
