@@ -12,6 +12,8 @@
 // elementwise warpgroups that take alternate blocks (each owns one S/dP TMEM buffer and one P/dS smem buffer), so
 // the exp2/convert work of block n overlaps the MMAs of block n+1.  The operands that must be read "transposed"
 // (dO_i, Q_i for dV/dK; K_j for dQ) are consumed in place as MN-major UMMA operands - nothing is transposed in smem.
+// Replaces the flash-attn-2 backward the reference reaches through HF (attn_implementation="flash_attention_2",
+// /root/reference/GRPO/grpo.py:219; training step /root/reference/GRPO/grpo_trainer.py:652).
 #include "common.cuh"
 #include "kernels.h"
 

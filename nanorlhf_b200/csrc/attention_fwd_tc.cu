@@ -11,7 +11,10 @@
 //                               swizzled smem; rescales O in TMEM when needed; final O / l and LSE go straight to HBM
 // TMEM (512 cols): S_A[2] 0..127, S_B[2] 128..255, O_A 256..383, O_B 384..511.
 // SMEM: Q 64 KB + 3 x (K 16 KB + V 16 KB) + P 2 tiles x 2 buffers x 16 KB = 224 KB.
-// The mma.sync kernels in attention_varlen.cu remain the backward path and the oracle for this kernel.
+// The softmax never waits for the tensor pipe on the common path: P is double buffered (pv_done[X][b] guards reuse) and O is
+// only rescaled - which needs PV of the previous block retired - when a row maximum grew by more than 2^8.
+// Backward: attention_bwd_tc.cu.  Oracle: the mma.sync kernels in attention_varlen.cu.  Together they replace flash-attn-2
+// (attn_implementation="flash_attention_2", /root/reference/GRPO/grpo.py:219) on the training, log-prob and prefill paths.
 #include <cstdlib>
 
 #include "common.cuh"
@@ -52,7 +55,7 @@ struct AttnTcParams {
   long o_stride_t;
   int num_seqs, total_tokens, Hq, G;
   float scale_log2;
-  long long* prof;            // optional [grid][16] cycle counters (NRL_ATTN_PROF)
+  long long* prof;            // optional [grid][40] cycle counters (NRL_ATTN_PROFILE builds, bench/attn_prof.py)
   int dbg;                    // timing experiments only (NRL_ATTN_DBG): 1 skip S MMAs, 2 skip PV MMAs, 4 skip exps, 8 skip K/V loads
 };
 
