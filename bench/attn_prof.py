@@ -1,4 +1,8 @@
-"""Cycle accounting of the tcgen05 attention forward: per-role time spent in each mbarrier wait (clock64)."""
+"""Cycle accounting of the tcgen05 attention forward: per-role time spent in each mbarrier wait (clock64).
+
+Needs the instrumented build:  NRL_ATTN_PROFILE=1 python -m nanorlhf_b200.csrc.build  (production builds carry no
+clock reads; the counters then stay zero).  NRL_ATTN_DBG=<bits> knocks out S MMAs (1), PV MMAs (2), exps (4), K/V loads (8)
+for timing experiments -- results are wrong by construction, only the time is meaningful."""
 import math
 import os
 import sys
