@@ -82,3 +82,14 @@ def generate(n: int, model, tokenizer, prompts: Union[torch.Tensor, Sequence[Seq
         eng.sync_weights()
         return eng.generate(prompts, n, temperature, top_p, max_tokens, eos_id, pad_id, seed)
     return torch_generate(model, prompts, n, temperature, top_p, max_tokens, eos_id, pad_id, seed)
+
+
+def vllm_generate(*args, **kwargs) -> torch.Tensor:
+    """Drop-in name of the reference's rollout helper.  Both call shapes are accepted:
+    ``vllm_generate(n, model, tokenizer, prompts, temperature, max_tokens)`` (GRPO / RLOO / RAFT,
+    /root/reference/GRPO/grpo_trainer.py:122) and ``vllm_generate(model, tokenizer, prompts, temperature, max_tokens)``
+    (PPO / REINFORCE / ReMax, /root/reference/PPO/ppo_trainer.py:132).  There is no vLLM behind it: the resident
+    in-process sampler is used, nothing is written to disk and no engine is booted."""
+    if args and isinstance(args[0], int) and not isinstance(args[0], bool):
+        return generate(*args, **kwargs)
+    return generate(1, *args, **kwargs)

@@ -48,3 +48,20 @@ def test_entry_script_runs_offline(script, extra, tmp_path):
     r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert os.path.isdir(os.path.join(tmp_path, "checkpoint-2"))
+
+
+def test_reference_helper_names_are_importable():
+    """module-level helpers a reference user imports from the trainer module."""
+    import torch
+    from nanorlhf_b200.models.qwen2 import Qwen2Config, Qwen2ForCausalLM
+    from nanorlhf_b200.trainer import (INVALID_LOGPROB, PolicyAndValueWrapper, forward, state_to_device,  # noqa: F401
+                                       vllm_generate)
+    from nanorlhf_b200.utils.tokenizer import ByteTokenizer
+    assert INVALID_LOGPROB == 1.0
+    tok = ByteTokenizer()
+    m = Qwen2ForCausalLM.from_config(Qwen2Config.tiny(vocab_size=tok.vocab_size), torch.float32, seed=0)
+    prompts = [[5, 6, 7], [8, 9]]
+    a = vllm_generate(2, m, tok, prompts, 0.0, 4, backend="torch")            # GRPO-style call: n first
+    b = vllm_generate(m, tok, prompts, 0.0, 4, backend="torch")               # PPO-style call: n = 1
+    assert a.shape == (4, 4) and b.shape == (2, 4)
+    assert torch.equal(a[0], a[1]) and torch.equal(a[0], b[0])                # greedy: samples of a prompt coincide
