@@ -3,6 +3,12 @@
   python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torchrun, one rank per GPU)
   python bench.py --impl reference ...                      (the unmodified reference)
 
+Batch: the default is ``--mini-batches 8`` = 4 x 8 x 8 = 256 prompts (x 4 samples = 1024 sequences) per rank per update
+-- the reference's arithmetic with ``num_mini_batches`` halved from 16 -- so that the driver's ``--steps 20 --warmup 5`` (25 full
+updates) finishes inside its per-run limit at every N; ``global_batch`` in ``config`` says what was run and is the same for
+the 1-GPU bench and the 1/2/4/8 scaling runs.  ``--mini-batches 16`` is the reference's own 512 prompts per rank
+(BASELINE.md has that number too).
+
 One *step* = one full GRPO update through the public API (``GRPOTrainer.train_one_update``): in-process
 rollout of ``prompts_per_rank x 4`` samples with up to 1500 response tokens on the sm_100a sampler,
 DeBERTa-v3-large reward scoring, policy+ref log-prob pass, advantage estimation, and the
@@ -19,16 +25,15 @@ from __future__ import annotations
 import argparse
 import json
 import os
-import statistics
-import subprocess
 import sys
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-BASELINE_EPISODES_PER_S = 1.0      # reference README.md:36 "~1 s/episode" on 1 x A100-40G
+# The only throughput the reference publishes: README.md:36 "~1 s/episode" on 1 x A100-40G with real weights (BASELINE.md
+# section 1).  Different hardware, real (EOS-terminated, shorter) responses: context, not a like-for-like ratio.
+BASELINE_EPISODES_PER_S = 1.0
 
 
 def parse():
@@ -37,8 +42,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=1)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mini-batches", type=int, default=16,
-                    help="num_mini_batches: prompts per rank per update = 4 x 8 x this (reference default 16 -> 512)")
+    ap.add_argument("--mini-batches", type=int, default=8,
+                    help="num_mini_batches: prompts per rank per update = 4 x 8 x this (8 -> 256; the reference's 16 -> 512)")
     ap.add_argument("--response-length", type=int, default=1500)
     ap.add_argument("--samples", type=int, default=4)
     ap.add_argument("--model", default="1.5b", choices=["tiny", "1.5b", "7b"])
@@ -61,41 +66,6 @@ def reference_arm(args):
     return 0
 
 
-class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-
-    def __init__(self, gpu_index: int):
-        self.rows, self.proc, self.idx = [], None, gpu_index
-
-    def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.idx), "-lms", "500"], stdout=subprocess.PIPE, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
-    def stop(self):
-        if self.proc is not None:
-            self.proc.terminate()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
-        reasons = set()
-        for r in self.rows:
-            if len(r) >= 9:
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
-
-
 def main():
     args = parse()
     if args.impl == "reference":
@@ -111,7 +81,7 @@ def main():
     from nanorlhf_b200.parallel.comm import Comm
     from nanorlhf_b200.reward.model_reward import ModelReward
     from nanorlhf_b200.trainer import GRPOTrainer
-    from nanorlhf_b200.utils.callbacks import TrainerCallback
+    from nanorlhf_b200.utils.clocks import ClockSampler
     from nanorlhf_b200.utils.data import synthetic_token_dataset
     from nanorlhf_b200.utils.tokenizer import ByteTokenizer
     from dataclasses import dataclass
@@ -171,7 +141,7 @@ def main():
                   f"logprob {m.get('time/logprob_s', 0):.2f}s train {m.get('time/train_s', 0):.2f}s", file=sys.stderr, flush=True)
 
     # ---- timed region -------------------------------------------------------------------------------
-    clocks = ClockSampler(dev.index or 0)
+    clocks = ClockSampler(dev.index or 0, period_ms=500)
     comm.barrier()
     torch.cuda.synchronize()
     if comm.is_main:
@@ -182,6 +152,8 @@ def main():
     t0 = time.perf_counter()
     ev0.record()
     phase = {}
+    trainer.optimizer.pop_comm_ms()
+    opt_steps0 = trainer.optimizer._step
     for u in range(args.warmup + 1, args.warmup + args.steps + 1):
         m = one_update(u)
         for k, v in m.items():
@@ -193,9 +165,11 @@ def main():
     comm.barrier()
     dev_ms = ev0.elapsed_time(ev1)
     clock_info = clocks.stop() if comm.is_main else None
-    times = torch.tensor([dev_ms, (t1 - t0) * 1e3], dtype=torch.float64, device=dev)
+    comm_ms = trainer.optimizer.pop_comm_ms() / max(1, trainer.optimizer._step - opt_steps0)
+    times = torch.tensor([dev_ms, (t1 - t0) * 1e3, comm_ms] + [phase.get(k, 0.0) for k in sorted(phase)], dtype=torch.float64, device=dev)
     comm.all_reduce_(times, "max")
-    dev_ms, wall_ms = times.tolist()
+    dev_ms, wall_ms, comm_ms = times.tolist()[:3]
+    phase = dict(zip(sorted(phase), times.tolist()[3:]))          # max over ranks, like the headline
     episodes = prompts_per_rank * comm.world_size * args.steps
     value = episodes / (dev_ms / 1e3)
     e2e = episodes / (wall_ms / 1e3)
@@ -204,12 +178,16 @@ def main():
         line = {
             "metric": "episodes_per_sec", "value": value, "unit": "episodes/s", "n_gpus": comm.world_size,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": value / BASELINE_EPISODES_PER_S, "dtype": "bf16",
+            "scaling": "weak", "vs_baseline": value / BASELINE_EPISODES_PER_S,
+            "vs_baseline_note": "denominator = the reference README's ~1 episode/s on 1 x A100-40G with real weights (its only "
+                                "published throughput); not a same-box ratio -- see BASELINE.md section 3 for same-box anchors",
+            "dtype": "bf16",
             "data": "synthetic hh-rlhf-shaped token prompts; random-init weights (no network)",
             "impl": "ours",
             "config": {"model": {"1.5b": "Qwen2.5-1.5B (random init)", "7b": "Qwen2.5-7B (random init)", "tiny": "tiny"}[args.model],
                        "algorithm": "GRPO", "reward_model": args.reward + " (random init)", "lora": "r=64 + embed/lm_head",
-                       "global_batch": prompts_per_rank * comm.world_size, "samples_per_prompt": args.samples,
+                       "global_batch": prompts_per_rank * comm.world_size, "prompts_per_rank": prompts_per_rank,
+                       "sequences_per_rank": prompts_per_rank * args.samples, "samples_per_prompt": args.samples,
                        "seq_len": args.response_length, "prompt_len": "24-160", "parallelism": f"dp{comm.world_size}",
                        "comm": args.comm if comm.world_size > 1 else "none", "rollout_dtype": args.rollout_dtype,
                        "gradient_checkpointing": bool(args.grad_checkpointing),
@@ -220,6 +198,11 @@ def main():
             "clocks": clock_info,
             "phases_s_per_step": {k[5:-2]: v / args.steps for k, v in sorted(phase.items())},
             "rollout_tok_per_s_per_gpu": roll_tokens / max(phase.get("time/rollout_s", 1e-9), 1e-9),
+            "rollout_tok_per_s": comm.world_size * roll_tokens / max(phase.get("time/rollout_s", 1e-9), 1e-9),
+            # device time of the gradient collective per optimizer step (K-AR kernel + its two barriers; runs after the
+            # last micro-step's backward, so all of it is exposed), max over ranks; 0 on one GPU
+            "exposed_comm_ms_per_step": comm_ms,
+            "optimizer_steps_per_update": args.mini_batches,
         }
         print(json.dumps(line), flush=True)
     trainer.heartbeat.close()

@@ -72,7 +72,6 @@ if "ppo" in which:
     results["ppo_value_init_s"] = time.time() - t0
     run("ppo_1.5b", PPOTrainer(cfg, tok, policy, ref, ds, value_model=vm, reward_func=rf))
     del policy, ref, vm
-    engine._ENGINES.clear()
     torch.cuda.empty_cache()
 
 if "r1" in which:
@@ -92,7 +91,6 @@ if "r1" in which:
 
     run("sparse_grpo_7b_fp8_rollout", SparseGRPOTrainer(cfg, tok, policy, ref, ds, reward_func=RandomBinaryReward()))
     del policy, ref
-    engine._ENGINES.clear()
     torch.cuda.empty_cache()
 
 if "sweep" in which:
@@ -107,7 +105,6 @@ if "sweep" in which:
         ds = synthetic_token_dataset(128, shape.vocab_size - 2, 24, 96, seed=1)
         run(f"{name}_1.5b_host_offload", cls(cfg, tok, policy, ref, ds, reward_func=TokenIdReward(7)))
         del policy, ref
-        engine._ENGINES.clear()
         torch.cuda.empty_cache()
 
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)

@@ -9,6 +9,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from nanorlhf_b200.ops import native  # noqa: E402
+from nanorlhf_b200.utils.clocks import ClockSampler  # noqa: E402
 
 native.load()
 peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"bf16_tflops": 1590.0, "hbm_gbs": 6650.0}
@@ -36,15 +37,21 @@ shapes = [("qkv_decode", 2048, 2048, 1536), ("o_decode", 2048, 1536, 1536), ("ga
           ("down_decode", 2048, 1536, 8960), ("gate_up_train", 6912, 17920, 1536), ("down_train", 6912, 1536, 8960),
           ("gate_up_logprob", 50000, 17920, 1536), ("lm_head_decode", 2048, 151936, 1536), ("square_8k", 8192, 8192, 8192)]
 rows = []
+clk = ClockSampler(0).start()
 for name, M, N, K in shapes:
     a = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
     b = torch.randn(N, K, device="cuda", dtype=torch.bfloat16)
     out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
     fl = 2.0 * M * N * K
     row = {"name": name, "M": M, "N": N, "K": K}
-    for bn in (128, 192, 256, 0):                     # 0 = the dispatcher's own choice
-        key = f"bn{bn}" if bn else "auto"
-        ms = timeit(lambda: native.ext().gemm_bf16(a, b, None, out, bn))
+    for bn in ((128, 192, 256, 0) if os.environ.get('NRL_SKIP_2CTA') == '1' else (128, 192, 256, 512, 0)):                # 512 = cta_group::2 (256x256 per CTA pair); 0 = dispatcher's choice
+        key = {512: "2cta", 0: "auto"}.get(bn, f"bn{bn}")
+        try:
+            ms = timeit(lambda: native.ext().gemm_bf16(a, b, None, out, bn))
+        except Exception as e:  # noqa: BLE001 -- a variant that cannot run this shape is recorded, not fatal
+            row[f"ours_{key}_error"] = str(e)[:200]
+            torch.cuda.synchronize()
+            continue
         row[f"ours_{key}_ms"] = ms
         row[f"ours_{key}_tflops"] = fl / ms / 1e9
     ms = timeit(lambda: torch.matmul(a, b.t(), out=out))
@@ -75,5 +82,6 @@ row = {"name": "lmhead_logprob_fused", "T": T, "V": V, "d": d, "ours_ms": ms, "o
        "eager_chunked_ms": ms_e, "speedup": ms_e / ms, "ours_frac_of_measured_peak": 2.0 * T * V * d / ms / 1e9 / peaks["bf16_tflops"]}
 rows.append(row)
 print(json.dumps(row), flush=True)
+rows.append({"clocks": clk.stop()})
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 json.dump(rows, open(os.path.join(ROOT, "gpurun_out", "gemm_bench.json"), "w"), indent=1)

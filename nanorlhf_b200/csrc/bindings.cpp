@@ -395,7 +395,7 @@ std::tuple<torch::Tensor, torch::Tensor> value_loss(const torch::Tensor& vpred, 
 }
 
 void adamw_flat(torch::Tensor param, const torch::Tensor& grad, torch::Tensor m, torch::Tensor v, double lr, double beta1,
-                double beta2, double eps, double wd, int64_t step, double grad_scale) {
+                double beta2, double eps, double wd, int64_t step, double grad_scale, c10::optional<torch::Tensor> master) {
   TORCH_CHECK(param.is_cuda() && param.scalar_type() == torch::kBFloat16 && grad.scalar_type() == torch::kBFloat16);
   TORCH_CHECK(param.is_contiguous() && grad.is_contiguous() && m.is_contiguous() && v.is_contiguous());
   TORCH_CHECK(m.scalar_type() == v.scalar_type() && (m.scalar_type() == torch::kFloat32 || m.scalar_type() == torch::kBFloat16));
@@ -406,7 +406,13 @@ void adamw_flat(torch::Tensor param, const torch::Tensor& grad, torch::Tensor m,
   h.step_size = static_cast<float>(lr / (1.0 - std::pow(beta1, static_cast<double>(step))));
   h.inv_bc2 = static_cast<float>(1.0 / (1.0 - std::pow(beta2, static_cast<double>(step))));
   h.grad_scale = grad_scale;
-  check(nrl_adamw_flat(param.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(), param.numel(),
+  float* mw = nullptr;
+  if (master.has_value()) {
+    TORCH_CHECK(master->is_cuda() && master->scalar_type() == torch::kFloat32 && master->is_contiguous() &&
+                master->numel() == param.numel(), "master must be a contiguous fp32 copy of param");
+    mw = master->data_ptr<float>();
+  }
+  check(nrl_adamw_flat(param.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(), mw, param.numel(),
                        m.scalar_type() == torch::kBFloat16 ? 1 : 0, h, cur_stream()), "adamw_flat");
 }
 
@@ -641,7 +647,7 @@ nrl::AdamHyper make_hyper(double lr, double beta1, double beta2, double eps, dou
 void allreduce_adam(const std::vector<int64_t>& grad_ptrs, const std::vector<int64_t>& param_ptrs, int64_t grad_mc,
                     int64_t param_mc, torch::Tensor m, torch::Tensor v, int64_t lo, int64_t n, int64_t rank, double lr,
                     double beta1, double beta2, double eps, double wd, int64_t step, double grad_scale,
-                    bool use_multicast, int64_t max_blocks) {
+                    bool use_multicast, int64_t max_blocks, c10::optional<torch::Tensor> master) {
   TORCH_CHECK(grad_ptrs.size() == param_ptrs.size() && !grad_ptrs.empty());
   TORCH_CHECK(m.is_cuda() && m.is_contiguous() && v.is_contiguous() && m.numel() == n && v.numel() == n);
   c10::cuda::CUDAGuard guard(m.device());
@@ -651,8 +657,13 @@ void allreduce_adam(const std::vector<int64_t>& grad_ptrs, const std::vector<int
     g[i] = reinterpret_cast<const void*>(grad_ptrs[i]);
     p[i] = reinterpret_cast<void*>(param_ptrs[i]);
   }
+  float* mw = nullptr;
+  if (master.has_value()) {
+    TORCH_CHECK(master->is_cuda() && master->scalar_type() == torch::kFloat32 && master->is_contiguous() && master->numel() == n);
+    mw = master->data_ptr<float>();
+  }
   check(nrl_allreduce_adam(g.data(), p.data(), reinterpret_cast<const void*>(grad_mc), reinterpret_cast<void*>(param_mc),
-                           m.data_ptr(), v.data_ptr(), lo, n, static_cast<int>(g.size()), static_cast<int>(rank),
+                           m.data_ptr(), v.data_ptr(), mw, lo, n, static_cast<int>(g.size()), static_cast<int>(rank),
                            m.scalar_type() == torch::kBFloat16 ? 1 : 0, use_multicast ? 1 : 0,
                            make_hyper(lr, beta1, beta2, eps, wd, step, grad_scale), static_cast<int>(max_blocks), cur_stream()),
         "allreduce_adam");
@@ -733,7 +744,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gae_scan", &gae_scan, py::arg("rewards"), py::arg("values") = py::none(), py::arg("gamma") = 1.0, py::arg("lam") = 1.0);
   m.def("policy_loss", &policy_loss);
   m.def("value_loss", &value_loss);
-  m.def("adamw_flat", &adamw_flat);
+  m.def("adamw_flat", &adamw_flat, py::arg("param"), py::arg("grad"), py::arg("m"), py::arg("v"), py::arg("lr"), py::arg("beta1"),
+        py::arg("beta2"), py::arg("eps"), py::arg("wd"), py::arg("step"), py::arg("grad_scale") = 1.0, py::arg("master") = py::none());
   m.def("sample", &sample, py::arg("logits"), py::arg("temperature"), py::arg("top_p"), py::arg("seed"), py::arg("step"),
         py::arg("row_ids") = py::none(), py::arg("row_steps") = py::none(), py::arg("out") = py::none());
   m.def("kv_cache_write", &kv_cache_write, py::arg("k"), py::arg("v"), py::arg("k_cache"), py::arg("v_cache"),
@@ -751,7 +763,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("kv_cache_write_fp8", &kv_cache_write_fp8, py::arg("k"), py::arg("v"), py::arg("kq"), py::arg("vq"), py::arg("ks"), py::arg("vs"),
         py::arg("slot_mapping"), py::arg("src_index") = py::none());
   m.def("paged_decode_fp8", &paged_decode_fp8);
-  m.def("allreduce_adam", &allreduce_adam);
+  m.def("allreduce_adam", &allreduce_adam, py::arg("grad_ptrs"), py::arg("param_ptrs"), py::arg("grad_mc"), py::arg("param_mc"),
+        py::arg("m"), py::arg("v"), py::arg("lo"), py::arg("n"), py::arg("rank"), py::arg("lr"), py::arg("beta1"), py::arg("beta2"),
+        py::arg("eps"), py::arg("wd"), py::arg("step"), py::arg("grad_scale"), py::arg("use_multicast"), py::arg("max_blocks"),
+        py::arg("master") = py::none());
   m.def("allreduce_sum", &allreduce_sum);
   nrl::bind_runtime(m);
 }

@@ -93,8 +93,8 @@ NRL_DEVICE void adamw8(float (&p)[8], const float (&g)[8], float (&m)[8], float 
 // P2P variant.  lo / n in elements (multiples of 8); moments are indexed from 0 (the owner's shard).
 template <typename MomentT, int WORLD>
 __global__ void __launch_bounds__(256) allreduce_adam_p2p_kernel(PeerPtrs ptrs, MomentT* __restrict__ m,
-                                                                 MomentT* __restrict__ v, long lo, long n, int rank,
-                                                                 AdamHyper h) {
+                                                                 MomentT* __restrict__ v, float* __restrict__ master,
+                                                                 long lo, long n, int rank, AdamHyper h) {
   const long nvec = n / 8;
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < nvec;
        i += static_cast<long>(gridDim.x) * blockDim.x) {
@@ -114,12 +114,16 @@ __global__ void __launch_bounds__(256) allreduce_adam_p2p_kernel(PeerPtrs ptrs, 
       for (int j = 0; j < 8; ++j) g[j] += t[j];
     }
     float p8[8], m8[8], v8[8];
-    unpack8(*reinterpret_cast<const uint4*>(ptrs.param[rank] + e), p8);
+    // fp32 master copy of the owned shard (ZeRO-1): the bf16 parameter is only its rounded broadcast, so updates
+    // far below one bf16 ulp (lr 6e-6 on |w| ~ 0.02) accumulate instead of rounding away
+    if (master != nullptr) load_moment8<float>(master + i * 8, p8);
+    else unpack8(*reinterpret_cast<const uint4*>(ptrs.param[rank] + e), p8);
     load_moment8<MomentT>(m + i * 8, m8);
     load_moment8<MomentT>(v + i * 8, v8);
     adamw8(p8, g, m8, v8, h);
     store_moment8<MomentT>(m + i * 8, m8);
     store_moment8<MomentT>(v + i * 8, v8);
+    if (master != nullptr) store_moment8<float>(master + i * 8, p8);
     const uint4 out = pack8(p8);
 #pragma unroll
     for (int p = 0; p < WORLD; ++p) {
@@ -134,19 +138,21 @@ template <typename MomentT>
 __global__ void __launch_bounds__(256) allreduce_adam_mc_kernel(const __nv_bfloat16* grad_mc, __nv_bfloat16* param_mc,
                                                                 const __nv_bfloat16* __restrict__ param_local,
                                                                 MomentT* __restrict__ m, MomentT* __restrict__ v,
-                                                                long lo, long n, AdamHyper h) {
+                                                                float* __restrict__ master, long lo, long n, AdamHyper h) {
   const long nvec = n / 8;
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < nvec;
        i += static_cast<long>(gridDim.x) * blockDim.x) {
     const long e = lo + i * 8;
     float g[8], p8[8], m8[8], v8[8];
     unpack8(multimem_ld_reduce_bf16x8(grad_mc + e), g);
-    unpack8(*reinterpret_cast<const uint4*>(param_local + e), p8);
+    if (master != nullptr) load_moment8<float>(master + i * 8, p8);
+    else unpack8(*reinterpret_cast<const uint4*>(param_local + e), p8);
     load_moment8<MomentT>(m + i * 8, m8);
     load_moment8<MomentT>(v + i * 8, v8);
     adamw8(p8, g, m8, v8, h);
     store_moment8<MomentT>(m + i * 8, m8);
     store_moment8<MomentT>(v + i * 8, v8);
+    if (master != nullptr) store_moment8<float>(master + i * 8, p8);
     multimem_st_bf16x8(param_mc + e, pack8(p8));
   }
 }
@@ -179,15 +185,15 @@ __global__ void __launch_bounds__(256) allreduce_p2p_kernel(PeerPtrs ptrs, long 
 }
 
 template <typename MomentT>
-static cudaError_t launch_p2p(const PeerPtrs& ptrs, void* m, void* v, long lo, long n, int world, int rank,
+static cudaError_t launch_p2p(const PeerPtrs& ptrs, void* m, void* v, float* master, long lo, long n, int world, int rank,
                               const AdamHyper& h, int blocks, cudaStream_t s) {
   auto M = static_cast<MomentT*>(m);
   auto V = static_cast<MomentT*>(v);
   switch (world) {
-    case 1: allreduce_adam_p2p_kernel<MomentT, 1><<<blocks, 256, 0, s>>>(ptrs, M, V, lo, n, rank, h); break;
-    case 2: allreduce_adam_p2p_kernel<MomentT, 2><<<blocks, 256, 0, s>>>(ptrs, M, V, lo, n, rank, h); break;
-    case 4: allreduce_adam_p2p_kernel<MomentT, 4><<<blocks, 256, 0, s>>>(ptrs, M, V, lo, n, rank, h); break;
-    case 8: allreduce_adam_p2p_kernel<MomentT, 8><<<blocks, 256, 0, s>>>(ptrs, M, V, lo, n, rank, h); break;
+    case 1: allreduce_adam_p2p_kernel<MomentT, 1><<<blocks, 256, 0, s>>>(ptrs, M, V, master, lo, n, rank, h); break;
+    case 2: allreduce_adam_p2p_kernel<MomentT, 2><<<blocks, 256, 0, s>>>(ptrs, M, V, master, lo, n, rank, h); break;
+    case 4: allreduce_adam_p2p_kernel<MomentT, 4><<<blocks, 256, 0, s>>>(ptrs, M, V, master, lo, n, rank, h); break;
+    case 8: allreduce_adam_p2p_kernel<MomentT, 8><<<blocks, 256, 0, s>>>(ptrs, M, V, master, lo, n, rank, h); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
@@ -198,8 +204,8 @@ static cudaError_t launch_p2p(const PeerPtrs& ptrs, void* m, void* v, long lo, l
 using namespace nrl;
 
 extern "C" cudaError_t nrl_allreduce_adam(const void* const* grad_ptrs, void* const* param_ptrs, const void* grad_mc,
-                                          void* param_mc, void* m, void* v, long lo, long n, int world, int rank,
-                                          int moments_bf16, int use_multicast, AdamHyper h, int max_blocks,
+                                          void* param_mc, void* m, void* v, float* master, long lo, long n, int world,
+                                          int rank, int moments_bf16, int use_multicast, AdamHyper h, int max_blocks,
                                           cudaStream_t s) {
   if (n == 0) return cudaSuccess;
   if (n % 8 != 0 || lo % 8 != 0 || world > kMaxWorld) return cudaErrorInvalidValue;
@@ -211,10 +217,10 @@ extern "C" cudaError_t nrl_allreduce_adam(const void* const* grad_ptrs, void* co
     auto PL = static_cast<const __nv_bfloat16*>(param_ptrs[rank]);
     if (moments_bf16)
       allreduce_adam_mc_kernel<__nv_bfloat16><<<static_cast<int>(blocks), 256, 0, s>>>(
-          G, P, PL, static_cast<__nv_bfloat16*>(m), static_cast<__nv_bfloat16*>(v), lo, n, h);
+          G, P, PL, static_cast<__nv_bfloat16*>(m), static_cast<__nv_bfloat16*>(v), master, lo, n, h);
     else
       allreduce_adam_mc_kernel<float><<<static_cast<int>(blocks), 256, 0, s>>>(G, P, PL, static_cast<float*>(m),
-                                                                               static_cast<float*>(v), lo, n, h);
+                                                                               static_cast<float*>(v), master, lo, n, h);
     return cudaGetLastError();
   }
   PeerPtrs ptrs;
@@ -222,8 +228,8 @@ extern "C" cudaError_t nrl_allreduce_adam(const void* const* grad_ptrs, void* co
     ptrs.grad[i] = static_cast<const __nv_bfloat16*>(grad_ptrs[i]);
     ptrs.param[i] = static_cast<__nv_bfloat16*>(param_ptrs[i]);
   }
-  return moments_bf16 ? launch_p2p<__nv_bfloat16>(ptrs, m, v, lo, n, world, rank, h, static_cast<int>(blocks), s)
-                      : launch_p2p<float>(ptrs, m, v, lo, n, world, rank, h, static_cast<int>(blocks), s);
+  return moments_bf16 ? launch_p2p<__nv_bfloat16>(ptrs, m, v, master, lo, n, world, rank, h, static_cast<int>(blocks), s)
+                      : launch_p2p<float>(ptrs, m, v, master, lo, n, world, rank, h, static_cast<int>(blocks), s);
 }
 
 extern "C" cudaError_t nrl_allreduce_sum(void* const* buf_ptrs, long lo, long n, int world, int rank, float scale,

@@ -33,7 +33,7 @@ cudaError_t nrl_policy_loss(const float* new_lp, const float* old_lp, const floa
                             float* acc, cudaStream_t s);
 cudaError_t nrl_value_loss(const float* vpred, const float* vold, const float* ret, const uint8_t* mask, float clip,
                            long n, float* grad_unnorm, float* acc, cudaStream_t s);
-cudaError_t nrl_adamw_flat(void* param, const void* grad, void* m, void* v, long n, int moments_bf16,
+cudaError_t nrl_adamw_flat(void* param, const void* grad, void* m, void* v, float* master, long n, int moments_bf16,
                            nrl::AdamHyper h, cudaStream_t s);
 
 cudaError_t nrl_sample(const void* logits, int is_bf16, long row_stride, int rows, int V, float temperature,
@@ -53,7 +53,7 @@ cudaError_t nrl_paged_decode(const void* q, long q_stride_s, const void* k_cache
 
 extern "C" {
 cudaError_t nrl_allreduce_adam(const void* const* grad_ptrs, void* const* param_ptrs, const void* grad_mc, void* param_mc,
-                               void* m, void* v, long lo, long n, int world, int rank, int moments_bf16,
+                               void* m, void* v, float* master, long lo, long n, int world, int rank, int moments_bf16,
                                int use_multicast, nrl::AdamHyper h, int max_blocks, cudaStream_t s);
 cudaError_t nrl_allreduce_sum(void* const* buf_ptrs, long lo, long n, int world, int rank, float scale, int max_blocks,
                               cudaStream_t s);

@@ -175,17 +175,20 @@ NRL_DEVICE void adamw_update8(float (&p)[8], const float (&g)[8], float (&m)[8],
 
 template <typename MomentT>
 __global__ void adamw_flat_kernel(__nv_bfloat16* __restrict__ param, const __nv_bfloat16* __restrict__ grad,
-                                  MomentT* __restrict__ m, MomentT* __restrict__ v, long n, AdamHyper h) {
+                                  MomentT* __restrict__ m, MomentT* __restrict__ v, float* __restrict__ master, long n,
+                                  AdamHyper h) {
   const long nvec = n / 8;
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < nvec;
        i += static_cast<long>(gridDim.x) * blockDim.x) {
     float p8[8], g8[8], m8[8], v8[8];
-    MomentIO<__nv_bfloat16>::load8(param + i * 8, p8);
+    if (master != nullptr) MomentIO<float>::load8(master + i * 8, p8);      // fp32 master weights (see comm.cu)
+    else MomentIO<__nv_bfloat16>::load8(param + i * 8, p8);
     MomentIO<__nv_bfloat16>::load8(grad + i * 8, g8);
     MomentIO<MomentT>::load8(m + i * 8, m8);
     MomentIO<MomentT>::load8(v + i * 8, v8);
     adamw_update8(p8, g8, m8, v8, h);
     MomentIO<__nv_bfloat16>::store8(param + i * 8, p8);
+    if (master != nullptr) MomentIO<float>::store8(master + i * 8, p8);
     MomentIO<MomentT>::store8(m + i * 8, m8);
     MomentIO<MomentT>::store8(v + i * 8, v8);
   }
@@ -223,8 +226,8 @@ extern "C" cudaError_t nrl_value_loss(const float* vpred, const float* vold, con
   return cudaGetLastError();
 }
 
-extern "C" cudaError_t nrl_adamw_flat(void* param, const void* grad, void* m, void* v, long n, int moments_bf16,
-                                      AdamHyper h, cudaStream_t s) {
+extern "C" cudaError_t nrl_adamw_flat(void* param, const void* grad, void* m, void* v, float* master, long n,
+                                      int moments_bf16, AdamHyper h, cudaStream_t s) {
   if (n == 0) return cudaSuccess;
   if (n % 8 != 0) return cudaErrorInvalidValue;
   long blocks = (n / 8 + 255) / 256;
@@ -233,9 +236,9 @@ extern "C" cudaError_t nrl_adamw_flat(void* param, const void* grad, void* m, vo
   auto G = static_cast<const __nv_bfloat16*>(grad);
   if (moments_bf16)
     adamw_flat_kernel<__nv_bfloat16><<<static_cast<int>(blocks), 256, 0, s>>>(
-        P, G, static_cast<__nv_bfloat16*>(m), static_cast<__nv_bfloat16*>(v), n, h);
+        P, G, static_cast<__nv_bfloat16*>(m), static_cast<__nv_bfloat16*>(v), master, n, h);
   else
     adamw_flat_kernel<float><<<static_cast<int>(blocks), 256, 0, s>>>(P, G, static_cast<float*>(m),
-                                                                       static_cast<float*>(v), n, h);
+                                                                       static_cast<float*>(v), master, n, h);
   return cudaGetLastError();
 }

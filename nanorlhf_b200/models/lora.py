@@ -180,6 +180,8 @@ class PeftModel(nn.Module):
         with torch.no_grad():
             for k, p in own.items():
                 p.copy_(sd[k].to(p.device, p.dtype))
+        # a resident sampler merged the previous adapter: make it re-merge before the next rollout
+        self.base_model._nrl_version = getattr(self.base_model, "_nrl_version", 0) + 1
 
     def save_pretrained(self, path: str, **_):
         from .hf_io import save_state_dict

@@ -312,9 +312,9 @@ def value_loss(vpred, values_old, returns, mask, cliprange_value):
     return loss, clipfrac
 
 
-def adamw_flat(param, grad, m, v, lr, beta1, beta2, eps, wd, step, scale=1.0):
+def adamw_flat(param, grad, m, v, lr, beta1, beta2, eps, wd, step, scale=1.0, master=None):
     _count()
-    ext().adamw_flat(param, grad, m, v, lr, beta1, beta2, eps, wd, step, scale)
+    ext().adamw_flat(param, grad, m, v, lr, beta1, beta2, eps, wd, step, scale, master)
 
 
 # --------------------------------------------------------------------------------------------

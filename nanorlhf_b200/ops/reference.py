@@ -263,18 +263,21 @@ def value_loss(vpred, values_old, returns, mask, cliprange_value: float):
 # --------------------------------------------------------------------------------------------
 # optimizer / sampling
 # --------------------------------------------------------------------------------------------
-def adamw_step_(p, g, m, v, lr, beta1, beta2, eps, wd, step, grad_scale: float = 1.0):
-    """In-place decoupled AdamW on one tensor; moments may be fp32 while p is bf16."""
+def adamw_step_(p, g, m, v, lr, beta1, beta2, eps, wd, step, grad_scale: float = 1.0, master=None):
+    """In-place decoupled AdamW on one tensor; moments may be fp32 while p is bf16.  ``master`` (fp32, same shape)
+    is the authoritative copy when given: p becomes its rounded image."""
     gf = g.float() * grad_scale
     m.mul_(beta1).add_(gf.to(m.dtype), alpha=1 - beta1)
     v.mul_(beta2).addcmul_(gf.to(v.dtype), gf.to(v.dtype), value=1 - beta2)
     bc1 = 1 - beta1 ** step
     bc2 = 1 - beta2 ** step
-    pf = p.float()
+    pf = p.float() if master is None else master
     if wd != 0.0:
         pf = pf * (1 - lr * wd)
     denom = (v.float() / bc2).sqrt_().add_(eps)
     pf = pf - (lr / bc1) * (m.float() / denom)
+    if master is not None:
+        master.copy_(pf)
     p.copy_(pf.to(p.dtype))
 
 

@@ -45,23 +45,26 @@ class FusedAllReduceAdam:
     def _mc(self, hdl) -> int:
         if self.use_multicast in ("0", "off", "never"):
             return 0
+        if self.use_multicast == "auto" and self.comm.world_size <= 2:
+            return 0          # measured (profiles/dist_check_2gpu_r1.json): at N=2 the P2P kernel is 1.6x faster than NVLS
+
         return int(getattr(hdl, "multicast_ptr", 0) or 0)
 
     @torch.no_grad()
     def allreduce_adam(self, f, hp: dict, scale: float):
         """reduce-scatter(grad) + AdamW on the owned shard + all-gather(param), one kernel."""
         gh, ph = self.handle(f.grad), self.handle(f.param)
+        from .optimizer import shard_bounds
         world, rank = self.comm.world_size, self.comm.rank
-        per = f.padded // world
-        lo = rank * per
-        n = per if rank < world - 1 else f.padded - lo
+        lo, hi = shard_bounds(f.padded, world, rank)
+        n = hi - lo
         mc_g, mc_p = self._mc(gh), self._mc(ph)
         use_mc = bool(mc_g and mc_p)
         gh.barrier(channel=0)                      # every rank's backward has finished writing its gradients
         native._count()
         native.ext().allreduce_adam(list(gh.buffer_ptrs), list(ph.buffer_ptrs), mc_g, mc_p, f.exp_avg, f.exp_avg_sq,
                                     lo, n, rank, hp["lr"], hp["beta1"], hp["beta2"], hp["eps"], hp["wd"], hp["step"],
-                                    scale, use_mc, self.max_blocks)
+                                    scale, use_mc, self.max_blocks, getattr(f, "master", None))
         ph.barrier(channel=1)                      # updated parameters are visible on every rank
         self.bytes_reduced += f.padded * f.grad.element_size()
 

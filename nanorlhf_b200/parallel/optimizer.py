@@ -17,7 +17,12 @@ B200-first design:
   peer's parameter buffer -- reduce-scatter + Adam + all-gather in one kernel, moments sharded
   ZeRO-1 style.  ``comm="nccl"`` keeps the baseline: ``dist.all_reduce`` then a local step.
 * moments are fp32 by default (``optimizer_state_dtype="bf16"`` reproduces the reference's
-  bf16-moment behaviour).
+  bf16-moment behaviour, SURVEY.md 7.4);
+* bf16 parameters get an **fp32 master copy of the owned shard** next to the moments (``master_weights``): at
+  the shipped lr = 6e-6 an Adam step (~lr) is far below half a bf16 ulp of a typical weight (|w| ~ 0.02 ->
+  ulp 1.2e-4), so without it ``round(p - lr * u)`` == p and training silently stalls.  peft keeps adapter
+  weights in fp32 for the same reason; here the model keeps bf16 compute copies and the optimizer owns the
+  fp32 truth (sharded 1/N per rank under fused DP, so it costs 4 bytes x 540 M / N).
 """
 from __future__ import annotations
 
@@ -58,12 +63,15 @@ class _Flat:
         self.state_dtype = state_dtype
         self.exp_avg = None
         self.exp_avg_sq = None
+        self.master = None
         self.shard = shard
 
-    def ensure_state(self, lo: int, hi: int):
+    def ensure_state(self, lo: int, hi: int, master: bool = False):
         if self.exp_avg is None:
             self.exp_avg = torch.zeros(hi - lo, dtype=self.state_dtype, device=self.device)
             self.exp_avg_sq = torch.zeros(hi - lo, dtype=self.state_dtype, device=self.device)
+        if master and self.master is None and self.dtype != torch.float32:
+            self.master = self.param[lo:hi].float()
 
     def rebind_grads(self):
         for p, off in zip(self.params, self.offsets):
@@ -75,14 +83,19 @@ class FusedAdamW(torch.optim.Optimizer):
     """AdamW over flat buffers; gradient averaging across data-parallel ranks happens inside step()."""
 
     def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0,
-                 state_dtype: torch.dtype = torch.float32, comm=None, comm_mode: str = "fused"):
+                 state_dtype: torch.dtype = torch.float32, comm=None, comm_mode: str = "fused",
+                 master_weights: bool = True):
         defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
         super().__init__(params, defaults)
         self.comm = comm
         self.world = comm.world_size if comm is not None else 1
         self.rank = comm.rank if comm is not None else 0
         self.comm_mode = comm_mode if self.world > 1 else "none"
+        if self.comm_mode == "fused" and self.world not in (2, 4, 8):
+            self.comm_mode = "nccl"          # csrc/comm.cu instantiates the P2P kernel for 2 / 4 / 8 ranks
         self.state_dtype = state_dtype
+        self.master_weights = master_weights
+        self.comm_events: List[tuple] = []      # (start, end) CUDA events around every collective of step()
         self._flats: List[_Flat] = []
         self._fused = None
         self._step = 0
@@ -123,8 +136,7 @@ class FusedAdamW(torch.optim.Optimizer):
         """Slice of the flat buffer whose moments this rank owns (whole buffer unless fused DP)."""
         if self.comm_mode != "fused":
             return 0, f.padded
-        per = f.padded // self.world
-        return self.rank * per, (self.rank + 1) * per if self.rank < self.world - 1 else f.padded
+        return shard_bounds(f.padded, self.world, self.rank)
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -133,23 +145,44 @@ class FusedAdamW(torch.optim.Optimizer):
             if f is None:
                 continue
             lo, hi = self._shard_bounds(f)
-            f.ensure_state(lo, hi)
+            f.ensure_state(lo, hi, self.master_weights)
             b1, b2 = g["betas"]
             hp = dict(lr=float(g["lr"]), beta1=b1, beta2=b2, eps=g["eps"], wd=g["weight_decay"], step=self._step)
+            timed = self.world > 1 and f.param.is_cuda
+            if timed:
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev0.record()
             if self.comm_mode == "fused":
                 self._fused.allreduce_adam(f, hp, self.grad_scale / self.world)
             else:
                 if self.comm_mode == "nccl":
                     self.comm.all_reduce_(f.grad, "sum")
                     scale = self.grad_scale / self.world
+                    if timed:                   # baseline: only the all-reduce is communication
+                        ev1.record()
+                        self.comm_events.append((ev0, ev1))
+                        timed = False
                 else:
                     scale = self.grad_scale
                 if ops.use_native(f.param):
-                    ops._nat().adamw_flat(f.param, f.grad, f.exp_avg, f.exp_avg_sq, scale=scale, **hp)
+                    ops._nat().adamw_flat(f.param, f.grad, f.exp_avg, f.exp_avg_sq, scale=scale, master=f.master, **hp)
                 else:
                     ref.adamw_step_(f.param, f.grad, f.exp_avg, f.exp_avg_sq, hp["lr"], b1, b2, hp["eps"], hp["wd"],
-                                    self._step, grad_scale=scale)
+                                    self._step, grad_scale=scale, master=f.master)
+            if timed:
+                ev1.record()
+                self.comm_events.append((ev0, ev1))
         return None
+
+    def pop_comm_ms(self) -> float:
+        """Device time spent in step()'s collectives since the last call (K-AR: the fused kernel + its two
+        barriers -- all of it is exposed, nothing overlaps it).  Synchronises on the recorded events."""
+        ms = 0.0
+        for a, b in self.comm_events:
+            b.synchronize()
+            ms += a.elapsed_time(b)
+        self.comm_events.clear()
+        return ms
 
     def grad_norm(self) -> torch.Tensor:
         sq = sum((f.grad.float() ** 2).sum() for f in self.flats)
@@ -162,31 +195,61 @@ class FusedAdamW(torch.optim.Optimizer):
             if f is not None and f.exp_avg is not None:
                 out[f"group{i}.exp_avg"] = f.exp_avg
                 out[f"group{i}.exp_avg_sq"] = f.exp_avg_sq
+                if f.master is not None:
+                    out[f"group{i}.master"] = f.master
         return out
 
     def set_state_tensor(self, key: str, t: torch.Tensor):
         gi, name = key.split(".")
         setattr(self._flats[int(gi[5:])], name, t)
 
-    def state_dict(self):
-        return {"step": self._step, "world": self.world, "comm_mode": self.comm_mode,
+    def state_dict(self, full: bool = False):
+        """``full=False``: this rank's shard (cheap, what the offload engine moves).  ``full=True``: the whole-buffer
+        state gathered from the owners -- the world-size independent form written to ``optimizer.pt``; collective."""
+        state = {k: v.detach() for k, v in self.state_tensors().items()}
+        layout = {"world": self.world, "comm_mode": self.comm_mode}
+        if full and self.comm_mode == "fused":
+            gathered = {}
+            for k, v in state.items():
+                f = self._flats[int(k.split(".")[0][5:])]
+                gathered[k] = self.comm.all_gather_cat(v)[:f.padded]
+            state, layout = gathered, {"world": 1, "comm_mode": "full"}
+        return {"step": self._step, **layout,
                 "param_groups": [{k: v for k, v in g.items() if k != "params"} for g in self.param_groups],
-                "state": {k: v.detach().cpu() for k, v in self.state_tensors().items()}}
+                "state": {k: v.cpu() for k, v in state.items()}}
 
     def load_state_dict(self, sd):
         self._step = sd["step"]
         for g, saved in zip(self.param_groups, sd["param_groups"]):
             g.update({k: v for k, v in saved.items() if k in ("lr", "betas", "eps", "weight_decay", "initial_lr")})
-        if sd.get("world", 1) != self.world or sd.get("comm_mode", "none") != self.comm_mode:
-            if sd["state"]:
-                print("[optimizer] checkpoint was written with a different DP layout; moments reset")
-            return
+        same_layout = sd.get("world", 1) == self.world and sd.get("comm_mode", "none") == self.comm_mode
         for k, v in sd["state"].items():
-            gi = int(k.split(".")[0][5:])
+            gi, name = int(k.split(".")[0][5:]), k.split(".")[1]
             f = self._flats[gi]
             lo, hi = self._shard_bounds(f)
-            f.ensure_state(lo, hi)
-            getattr(f, k.split(".")[1]).copy_(v.to(f.device))
+            f.ensure_state(lo, hi, self.master_weights and name == "master")
+            dst = getattr(f, name)
+            if dst is None:
+                continue
+            if v.numel() == f.padded:                       # whole-buffer state: take the slice this rank owns
+                dst.copy_(v[lo:hi].to(f.device))
+            elif same_layout and v.numel() == dst.numel():
+                dst.copy_(v.to(f.device))
+            else:
+                raise RuntimeError(f"optimizer state '{k}' has {v.numel()} elements: a per-rank shard written with a "
+                                   f"different DP layout (world {sd.get('world')}); save with state_dict(full=True) to reshard")
+        for f in self.flats:                                # the bf16 parameters are the rounded image of the master copy
+            if f.master is not None and any(k.endswith(".master") for k in sd["state"]):
+                lo, hi = self._shard_bounds(f)
+                f.param[lo:hi].copy_(f.master.to(f.dtype))
+
+
+def shard_bounds(padded: int, world: int, rank: int):
+    """[lo, hi) of the flat buffer owned by ``rank``: equal slices rounded down to 8 elements (the kernels move
+    16-byte vectors, any world size), the last rank takes the remainder."""
+    per = (padded // world) // 8 * 8
+    lo = rank * per
+    return lo, (lo + per if rank < world - 1 else padded)
 
 
 def build_param_groups(named_params: Iterable, weight_decay: float, lr: float):

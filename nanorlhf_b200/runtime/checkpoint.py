@@ -46,8 +46,7 @@ def save_model(trainer, output_dir: str):
         _save_one_model(trainer.model.value_model, os.path.join(output_dir, "value_model"))
     if hasattr(trainer.tokenizer, "save_pretrained"):
         trainer.tokenizer.save_pretrained(output_dir)
-    with open(os.path.join(output_dir, "training_args.bin"), "wb") as f:
-        pickle.dump(trainer.args.to_dict(), f)
+    torch.save(trainer.args.to_dict(), os.path.join(output_dir, "training_args.bin"))      # torch.load-able like HF's
 
 
 def _rng_state(device):
@@ -66,11 +65,13 @@ def save_checkpoint(trainer, metrics=None):
     comm.barrier()
     save_model(trainer, out)
     if not a.save_only_model:
-        opt_sd = trainer.optimizer.state_dict()
-        sharded = getattr(trainer.optimizer, "comm_mode", "none") == "fused" and comm.world_size > 1
-        if sharded:
-            torch.save(opt_sd, os.path.join(out, f"optimizer_rank{comm.rank}.pt"))
-        elif comm.is_main:
+        # one world-size independent optimizer.pt (reference layout): under fused DP the ZeRO-1 shards of the moments /
+        # fp32 master weights are gathered from their owners, so a run can resume on a different number of GPUs
+        try:
+            opt_sd = trainer.optimizer.state_dict(full=True)
+        except TypeError:                       # a user-supplied torch optimizer
+            opt_sd = trainer.optimizer.state_dict()
+        if comm.is_main:
             torch.save(opt_sd, os.path.join(out, "optimizer.pt"))
         if comm.is_main:
             torch.save(trainer.lr_scheduler.state_dict(), os.path.join(out, "scheduler.pt"))
@@ -155,7 +156,7 @@ def load_checkpoint(trainer, path: str):
     vdir = os.path.join(path, "value_model")
     if trainer.uses_value_model and os.path.isdir(vdir):
         _load_model_into(trainer.model.value_model, vdir)
-    opt_path = os.path.join(path, f"optimizer_rank{comm.rank}.pt")
+    opt_path = os.path.join(path, f"optimizer_rank{comm.rank}.pt")        # layout written by round-1 checkpoints
     if not os.path.exists(opt_path):
         opt_path = os.path.join(path, "optimizer.pt")
     if os.path.exists(opt_path):
@@ -175,6 +176,8 @@ def load_checkpoint(trainer, path: str):
         trainer._np_rng.set_state(rng["trainer_np_rng"])
         trainer._select_gen.set_state(rng["trainer_select_gen"])
         trainer.dataloader.load_state_dict(rng["dataloader"])
+    if hasattr(trainer, "_bump_policy_version"):
+        trainer._bump_policy_version()            # a resident sampler must re-merge: its arena predates these weights
     old = OnlineTrainerState.load_from_json(os.path.join(path, "trainer_state.json"))
     for k in ("global_step", "episode", "epoch", "log_history", "best_metric", "best_model_checkpoint"):
         setattr(trainer.state, k, getattr(old, k))

@@ -53,18 +53,25 @@ def _pick_backend(model, requested: str) -> str:
     return "native" if dev.type == "cuda" else "torch"
 
 
-_ENGINES = {}
-
-
 def get_native_engine(model, **kw):
-    """One persistent native engine per policy object (no boot/teardown per rollout)."""
+    """One persistent native engine per policy object (no boot/teardown per rollout).  The engine hangs off the
+    policy module itself, so its weight arena and KV pages are released with the model (no process-global cache);
+    ``release_native_engine`` frees them earlier."""
     from .native_sampler import NativeSampler
-    key = id(getattr(model, "policy", model))
-    eng = _ENGINES.get(key)
-    if eng is None:
+    pol = getattr(model, "policy", model)
+    eng = pol.__dict__.get("_nrl_sampler")
+    if eng is None or eng.rollout_dtype != kw.get("rollout_dtype", eng.rollout_dtype):
         eng = NativeSampler(model, **kw)
-        _ENGINES[key] = eng
+        pol.__dict__["_nrl_sampler"] = eng        # plain attribute: not a sub-module, not in state_dict
     return eng
+
+
+def release_native_engine(model):
+    """Drop the resident sampler of ``model`` (weight arena, KV pages, CUDA graphs)."""
+    pol = getattr(model, "policy", model)
+    eng = pol.__dict__.pop("_nrl_sampler", None)
+    if eng is not None:
+        eng.release()
 
 
 def generate(n: int, model, tokenizer, prompts: Union[torch.Tensor, Sequence[Sequence[int]]], temperature: float,

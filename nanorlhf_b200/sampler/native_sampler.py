@@ -103,6 +103,11 @@ class NativeSampler:
                 native._count()
                 lw.q8[name] = native.ext().quant_rows_e4m3(getattr(lw, name))
 
+    def release(self):
+        """Free the arena, the KV pages and the captured graphs (the engine is unusable afterwards)."""
+        self._graphs.clear()
+        self.layers, self.k_cache, self.v_cache, self.num_blocks = [], [], [], 0
+
     def weights_fingerprint(self):
         """Cheap change detector: the optimizer bumps ``_nrl_version`` on the policy after every step."""
         return getattr(self.lm, "_nrl_version", 0)

@@ -285,14 +285,16 @@ class RLTrainer:
             metrics = self.train_one_update(update, next(it))
             self.lr_scheduler.step()
             self.control = self.callback_handler.on_step_end(a, self.state, self.control)
-            # the reference's flow callback would stop at max_steps = batches*minibatches which is
-            # never reached (SURVEY.md 3.5 "Schedules"); the loop bound is authoritative here.
-            self.control.should_training_stop = False
+            # state.max_steps = batches * minibatches is never reached by global_step (SURVEY.md 3.5 "Schedules"),
+            # so the flow callback cannot stop the loop early; a stop raised by any *other* callback (early stopping,
+            # a user callback) is honoured after this update's checkpoint.
             if self.control.should_save:
                 with self.timer.phase("ckpt"):
                     self._save_checkpoint(self.model, trial=None, metrics=metrics)
                 self.control = self.callback_handler.on_save(a, self.state, self.control)
             self.after_update(update, metrics)
+            if self.control.should_training_stop:
+                break
         self.control = self.callback_handler.on_train_end(a, self.state, self.control)
         if self.control.should_save:
             self._save_checkpoint(self.model, trial=None, metrics=metrics)
@@ -419,16 +421,22 @@ class RLTrainer:
         a = self.args
         ctx = batch["context_length"]
         pad = self.tokenizer.pad_token_id
-        shape = (a.num_ppo_epochs, a.num_mini_batches, a.gradient_accumulation_steps)
         n_local = batch["responses"].shape[0]
+        # The number of optimizer steps per update is ``num_mini_batches`` whatever the number of trained rows (the LR
+        # schedule and ``max_steps`` assume it): with ``train_samples_per_prompt = N`` the rows -- hence the local
+        # mini-batch and its gradient-accumulation depth -- grow N-fold instead of the step count.
+        lmb = max(a.per_device_train_batch_size, -(-n_local // a.num_mini_batches))
+        accum = -(-lmb // a.per_device_train_batch_size)
+        self._accum_steps = accum
+        shape = (a.num_ppo_epochs, -(-n_local // lmb), accum)
         graphed = self._graph_micro_step()
         keys = graphed.stat_keys if graphed is not None else None
         rows = {}
         self.policy.train()
         for ep in range(a.num_ppo_epochs):
             b_inds = self._np_rng.permutation(n_local)
-            for mi, mb_start in enumerate(range(0, n_local, a.local_mini_batch_size)):
-                mini = b_inds[mb_start:mb_start + a.local_mini_batch_size]
+            for mi, mb_start in enumerate(range(0, n_local, lmb)):
+                mini = b_inds[mb_start:mb_start + lmb]
                 self.optimizer.zero_grad()
                 for gi, mc_start in enumerate(range(0, len(mini), a.per_device_train_batch_size)):
                     inds = torch.as_tensor(mini[mc_start:mc_start + a.per_device_train_batch_size], device=self.device)
@@ -446,7 +454,7 @@ class RLTrainer:
                     if self.uses_value_model:
                         mb["vpred"] = out[2]
                     loss, st = self.micro_loss(mb)
-                    (loss / a.gradient_accumulation_steps).backward()
+                    (loss / accum).backward()
                     with torch.no_grad():
                         ent = out[1]
                         if a.stats_include_padding:

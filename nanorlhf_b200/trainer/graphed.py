@@ -51,14 +51,14 @@ class GraphedMicroStep:
         self.disabled = False
 
     # ---- the device-only micro-step ---------------------------------------------------------------
-    def _body(self, plan, mb, B, T_r, L):
+    def _body(self, plan, mb, B, T_r, L, accum):
         t, a = self.t, self.t.args
         out_lp, out_ent, _ = planned_response_logprobs(t.policy, plan, B, T_r, a.temperature, True,
                                                        max_seqlen=L)
         mb = dict(mb)
         mb["new_logprobs"] = torch.masked_fill(out_lp, mb["padding_mask"], INVALID_LOGPROB)
         loss, st = t.micro_loss(mb)
-        (loss / a.gradient_accumulation_steps).backward()
+        (loss / accum).backward()
         with torch.no_grad():
             if a.stats_include_padding:
                 st["entropy"] = out_ent.mean()
@@ -104,7 +104,8 @@ class GraphedMicroStep:
         T_b = _round_up(plan["ids"].numel(), TOKEN_BUCKET)
         R_b = _round_up(max(plan["src"].numel(), 1), ROW_BUCKET)
         tens = {k: v for k, v in mb.items() if isinstance(v, torch.Tensor) and k != "query_responses"}
-        key = (T_b, R_b, B, L, tuple(sorted((k, tuple(v.shape), str(v.dtype)) for k, v in tens.items())))
+        accum = int(getattr(self.t, "_accum_steps", self.t.args.gradient_accumulation_steps))
+        key = (T_b, R_b, B, L, accum, tuple(sorted((k, tuple(v.shape), str(v.dtype)) for k, v in tens.items())))
         padded = self._pad_plan(plan, B, pad_id, T_b, R_b)
         cap = self.graphs.get(key)
         if cap is None:
@@ -112,16 +113,16 @@ class GraphedMicroStep:
             self.seen[key] = n + 1
             if n == 0 or self.disabled or len(self.graphs) >= MAX_GRAPHS:
                 self.eager += 1
-                return self._body(padded, tens, B, T_r, L)           # eager (also the capture warm-up)
+                return self._body(padded, tens, B, T_r, L, accum)    # eager (also the capture warm-up)
             try:
-                cap = self._capture(key, padded, tens, B, T_r, L)
+                cap = self._capture(key, padded, tens, B, T_r, L, accum)
             except Exception as e:  # noqa: BLE001 -- a step that cannot be captured must still train
                 import warnings
                 warnings.warn(f"CUDA-graph capture of the micro-step failed ({type(e).__name__}: {e}); "
                               "using eager micro-steps from now on")
                 self.disabled = True                  # capture records, it does not execute: .grad is untouched
                 self.eager += 1
-                return self._body(padded, tens, B, T_r, L)
+                return self._body(padded, tens, B, T_r, L, accum)
         else:
             self.graphs.move_to_end(key)
         for k, v in padded.items():
@@ -134,7 +135,7 @@ class GraphedMicroStep:
         native._count(cap.launches)
         return cap.out.clone()
 
-    def _capture(self, key, padded, tens, B, T_r, L) -> _Captured:
+    def _capture(self, key, padded, tens, B, T_r, L, accum) -> _Captured:
         from ..ops import native
         cap = _Captured()
         cap.plan = {k: v.clone() for k, v in padded.items()}
@@ -145,7 +146,7 @@ class GraphedMicroStep:
         before = native.launches()
         cap.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(cap.graph, pool=self.pool):
-            cap.out = self._body(cap.plan, cap.mb, B, T_r, L)
+            cap.out = self._body(cap.plan, cap.mb, B, T_r, L, accum)
         cap.launches = native.launches() - before
         native._count(-cap.launches)                # capture launched nothing; replays add it back
         self.graphs[key] = cap

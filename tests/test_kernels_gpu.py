@@ -474,3 +474,25 @@ def test_paged_decode_fp8_kv(Hq, Hkv, splits):
     out = n.ext().paged_decode_fp8(q, kq, vq, ks, vs, table, ctx, 1.0 / math.sqrt(D), splits)
     want = ref.paged_attention_decode(q, kd, vd, table, ctx)      # oracle on the dequantised cache
     assert _rel(out, want) < 2e-2
+
+
+def test_adamw_flat_master_weights_lr_6e6():
+    """at lr = 6e-6 bf16 parameters stall without an fp32 master copy; with it the kernel tracks
+    torch.optim.AdamW (fp32) over 100 steps."""
+    n = _native()
+    torch.manual_seed(0)
+    N = 8192
+    w0 = (torch.rand(N, device="cuda") * 0.05 - 0.025).bfloat16()
+    p, master = w0.clone(), w0.float()
+    m, v = torch.zeros(N, device="cuda"), torch.zeros(N, device="cuda")
+    refp = torch.nn.Parameter(w0.float().clone())
+    ropt = torch.optim.AdamW([refp], lr=6e-6, weight_decay=0.0)
+    for step in range(1, 101):
+        g = (torch.randn(N, device="cuda") + 0.5).bfloat16()
+        n.adamw_flat(p, g, m, v, 6e-6, 0.9, 0.999, 1e-8, 0.0, step, 1.0, master)
+        refp.grad = g.float()
+        ropt.step()
+    want = (refp.detach() - w0.float()).abs().mean()
+    got = (master - w0.float()).abs().mean()
+    assert abs(got - want) / want < 0.02
+    assert torch.equal(p, master.bfloat16())

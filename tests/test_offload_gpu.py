@@ -45,7 +45,6 @@ def test_trainer_with_host_offloaded_roles_matches_resident(tmp_path):
     outs = []
     for policy_kind in ("resident", "host"):
         engine.reseed_stream(42)
-        engine._ENGINES.clear()
         policy = get_peft_model(Qwen2ForCausalLM.from_config(cfg, torch.bfloat16, dev, seed=1), LoraConfig(r=8, lora_alpha=16, modules_to_save=None))
         with torch.no_grad():
             g = torch.Generator(device=dev).manual_seed(3)

@@ -119,3 +119,14 @@ def test_value_initializer(tmp_path):
     hist = out.value_init_history
     assert len(hist) >= 2 and min(h["eval_loss"] for h in hist) <= hist[0]["eval_loss"]
     assert any(not torch.equal(a, b) for a, b in zip(before, [p for p in vm.parameters() if p.requires_grad]))
+
+
+def test_train_on_all_samples_keeps_step_count(tmp_path):
+    """``train_samples_per_prompt = N`` (train on every sample): N x the rows, the same number of optimizer steps, no
+    out-of-range stats slot."""
+    t = build(GRPOTrainer, tmp_path, {"grpo_sample_N": 4}, train_samples_per_prompt=4)
+    steps0 = t.optimizer._step
+    m = t.train()
+    assert t.state.global_step == 2
+    assert t.optimizer._step - steps0 == 2 * t.args.num_mini_batches
+    assert all(k in m for k in GRPO_KEYS)

@@ -16,7 +16,6 @@ def _setup(tmp_path, cls, extra=None, **kw):
     from nanorlhf_b200.trainer import PPOTrainer
     from nanorlhf_b200.utils.data import synthetic_token_dataset
     from nanorlhf_b200.utils.tokenizer import ByteTokenizer
-    engine._ENGINES.clear()
     dev = torch.device("cuda")
     cfg = Qwen2Config(vocab_size=4096, hidden_size=256, intermediate_size=512, num_hidden_layers=2, num_attention_heads=4,
                       num_key_value_heads=2, head_dim=128)
