@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "gemm_sm100.h"
+#include "gemm_tc.h"
 #include "kernels.h"
 #include "runtime.h"
 #include "tma_host.h"
@@ -98,6 +99,111 @@ torch::Tensor gemm_bf16(const torch::Tensor& a, const torch::Tensor& b, const c1
     p.bias = reinterpret_cast<const __nv_bfloat16*>(bias->data_ptr());
   }
   check(nrl_gemm_bf16_tn(&tmA, &tmB, &tmD, &p, bn, nrl::EPI_STORE, num_sms(), cur_stream()), "gemm_bf16");
+  return out;
+}
+
+// ---- general tcgen05 GEMM (gemm_tc.cu) ---------------------------------------------------------------------------
+// Tile-shape choice: expected throughput of a candidate = (per-tile efficiency measured on B200, profiles/gemm_bench_r2.json)
+// x (useful fraction of the padded M and N) x (tiles / (waves x units)).  CG = 2 halves the number of scheduling units.
+struct TcChoice { int cg, bn; };
+TcChoice pick_tc_tile(int64_t M, int64_t N, bool a_mn, bool b_mn, bool f32_out) {
+  struct Cand { int cg, bn; double eff; };
+  static const Cand all[] = {{2, 256, 1.00}, {2, 192, 0.95}, {2, 128, 0.82}, {1, 256, 0.86}, {1, 192, 0.80}, {1, 128, 0.72}, {1, 64, 0.45}};
+  const int sms = num_sms();
+  TcChoice best{1, 128};
+  double best_s = -1.0;
+  for (const Cand& c : all) {
+    if (b_mn && (c.bn / c.cg) % 64 != 0) continue;                       // MN-major B tiles are made of 64-column panels
+    if (a_mn && !((c.cg == 1 && c.bn != 192) || (c.cg == 2 && c.bn == 256))) continue;      // instantiated wgrad shapes
+    if (!a_mn && b_mn && c.cg == 2 && c.bn == 192) continue;
+    if (f32_out && !a_mn) continue;
+    const int64_t tm = c.cg * 128;
+    const int64_t num_m = (M + tm - 1) / tm, num_n = (N + c.bn - 1) / c.bn, tiles = num_m * num_n;
+    const int64_t units = sms / c.cg, waves = (tiles + units - 1) / units;
+    const double s = c.eff * (static_cast<double>(M) / (num_m * tm)) * (static_cast<double>(N) / (num_n * c.bn)) *
+                     (static_cast<double>(tiles) / (waves * units));
+    if (s > best_s) { best_s = s; best = {c.cg, c.bn}; }
+  }
+  return best;
+}
+
+inline void check_tc_operand(const torch::Tensor& t, const char* name) {
+  TORCH_CHECK(t.is_cuda() && t.scalar_type() == torch::kBFloat16 && t.dim() == 2, name, " must be a 2D CUDA bf16 tensor");
+  TORCH_CHECK(t.stride(1) == 1 && (t.stride(0) * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(t.data_ptr()) & 15) == 0,
+              name, " must have unit inner stride and 16-byte aligned rows");
+}
+
+// D[M,N] = alpha * (opA(a) opB(b)^T + opA(a2) opB(b2)^T) (+bias) (GELU).
+//   a_mn = false: a is [M, K] (contraction contiguous);  a_mn = true: a is [K, M] (contraction = rows).  Same for b / N.
+//   Output: bf16 `out` [M, N] (allocated when absent) or, when `out_f32` is given, fp32 out_f32 (+)= result.
+torch::Tensor gemm_tc(const torch::Tensor& a, const torch::Tensor& b, bool a_mn, bool b_mn, const c10::optional<torch::Tensor>& a2,
+                      const c10::optional<torch::Tensor>& b2, const c10::optional<torch::Tensor>& bias, int64_t act, double alpha,
+                      c10::optional<torch::Tensor> out_opt, c10::optional<torch::Tensor> out_f32, bool accumulate, int64_t cg_req,
+                      int64_t bn_req) {
+  check_tc_operand(a, "a");
+  check_tc_operand(b, "b");
+  const int64_t M = a_mn ? a.size(1) : a.size(0), K = a_mn ? a.size(0) : a.size(1);
+  const int64_t N = b_mn ? b.size(1) : b.size(0);
+  TORCH_CHECK((b_mn ? b.size(0) : b.size(1)) == K, "gemm_tc: contraction lengths of a and b differ");
+  TORCH_CHECK(N % 8 == 0, "gemm_tc: N must be a multiple of 8");      // operand alignment is checked per tensor (row strides)
+  int64_t K2 = 0;
+  if (a2.has_value() || b2.has_value()) {
+    TORCH_CHECK(a2.has_value() && b2.has_value(), "gemm_tc: a2 and b2 go together");
+    check_tc_operand(*a2, "a2");
+    check_tc_operand(*b2, "b2");
+    K2 = a_mn ? a2->size(0) : a2->size(1);
+    TORCH_CHECK((a_mn ? a2->size(1) : a2->size(0)) == M && (b_mn ? b2->size(1) : b2->size(0)) == N &&
+                (b_mn ? b2->size(0) : b2->size(1)) == K2, "gemm_tc: second operand pair has the wrong shape");
+  }
+  c10::cuda::CUDAGuard guard(a.device());
+  const bool f32 = out_f32.has_value();
+  torch::Tensor out;
+  if (f32) {
+    TORCH_CHECK(out_f32->is_cuda() && out_f32->scalar_type() == torch::kFloat32 && out_f32->dim() == 2 && out_f32->size(0) == M &&
+                out_f32->size(1) == N && out_f32->stride(1) == 1 && out_f32->stride(0) % 4 == 0 &&
+                (reinterpret_cast<uintptr_t>(out_f32->data_ptr()) & 15) == 0, "gemm_tc: out_f32 must be fp32 [M, N], 16-byte aligned rows");
+    TORCH_CHECK(!bias.has_value() && act == 0, "gemm_tc: the fp32 epilogue has no bias / activation");
+    out = *out_f32;
+  } else {
+    out = out_opt.has_value() ? *out_opt : torch::empty({M, N}, a.options());
+    check_tc_operand(out, "out");
+    TORCH_CHECK(out.size(0) == M && out.size(1) == N, "gemm_tc: out has the wrong shape");
+  }
+  if (M == 0 || N == 0) return out;
+  TcChoice ch = pick_tc_tile(M, N, a_mn, b_mn, f32);
+  if (cg_req > 0) ch.cg = static_cast<int>(cg_req);
+  if (bn_req > 0) ch.bn = static_cast<int>(bn_req);
+  const auto BF = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  auto map_a = [&](const torch::Tensor& t) {
+    return a_mn ? nrl::make_tma_2d(t.data_ptr(), t.size(0), t.size(1), t.stride(0) * 2, 64, 64, BF, 2)
+                : nrl::make_tma_2d(t.data_ptr(), t.size(0), t.size(1), t.stride(0) * 2, 128, 64, BF, 2);
+  };
+  auto map_b = [&](const torch::Tensor& t) {
+    return b_mn ? nrl::make_tma_2d(t.data_ptr(), t.size(0), t.size(1), t.stride(0) * 2, 64, 64, BF, 2)
+                : nrl::make_tma_2d(t.data_ptr(), t.size(0), t.size(1), t.stride(0) * 2, ch.bn / ch.cg, 64, BF, 2);
+  };
+  CUtensorMap maps[5];
+  maps[0] = map_a(a);
+  maps[1] = map_b(b);
+  maps[2] = K2 > 0 ? map_a(*a2) : maps[0];
+  maps[3] = K2 > 0 ? map_b(*b2) : maps[1];
+  maps[4] = f32 ? maps[0] : nrl::make_tma_2d(out.data_ptr(), M, N, out.stride(0) * 2, 128, 64, BF, 2);
+  nrl::tc::TcParams p{};
+  p.M = static_cast<int>(M); p.N = static_cast<int>(N); p.K = static_cast<int>(K); p.K2 = static_cast<int>(K2);
+  p.alpha = static_cast<float>(alpha);
+  p.act = static_cast<int>(act);
+  if (bias.has_value()) {
+    TORCH_CHECK(bias->is_cuda() && bias->scalar_type() == torch::kBFloat16 && bias->numel() == N && bias->is_contiguous(),
+                "bias must be a contiguous CUDA bf16 [N] tensor");
+    p.bias = reinterpret_cast<const __nv_bfloat16*>(bias->data_ptr());
+  }
+  if (f32) {
+    p.out_f32 = out.data_ptr<float>();
+    p.out_f32_stride = out.stride(0);
+    p.accumulate = accumulate ? 1 : 0;
+  }
+  check(nrl_gemm_tc(maps, &p, ch.cg, ch.bn, a_mn ? 1 : 0, b_mn ? 1 : 0, f32 ? nrl::tc::EPI_F32 : nrl::tc::EPI_BF16, num_sms(),
+                    cur_stream()), "gemm_tc (no kernel instantiated for this cg / block_n / operand-major combination?)");
   return out;
 }
 
@@ -724,6 +830,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "nanorlhf_b200 sm_100a kernels";
   m.def("gemm_bf16", &gemm_bf16, py::arg("a"), py::arg("b"), py::arg("bias") = py::none(), py::arg("out") = py::none(),
         py::arg("block_n") = 0, py::arg("act") = 0);
+  m.def("gemm_tc", &gemm_tc, py::arg("a"), py::arg("b"), py::arg("a_mn") = false, py::arg("b_mn") = false, py::arg("a2") = py::none(),
+        py::arg("b2") = py::none(), py::arg("bias") = py::none(), py::arg("act") = 0, py::arg("alpha") = 1.0, py::arg("out") = py::none(),
+        py::arg("out_f32") = py::none(), py::arg("accumulate") = false, py::arg("cg") = 0, py::arg("block_n") = 0);
   m.def("add_layernorm", &add_layernorm);
   m.def("lmhead_logprob_fwd", &lmhead_logprob_fwd, py::arg("hidden"), py::arg("weight"), py::arg("targets"),
         py::arg("inv_temperature"), py::arg("n_splits") = 0);

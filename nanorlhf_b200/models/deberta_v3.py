@@ -26,6 +26,9 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .. import ops
+from .qwen2 import Linear
+
 
 @dataclass
 class DebertaV3Config:
@@ -83,9 +86,9 @@ class DisentangledSelfAttention(nn.Module):
         super().__init__()
         self.h = cfg.num_attention_heads
         self.dh = cfg.hidden_size // cfg.num_attention_heads
-        self.query_proj = nn.Linear(cfg.hidden_size, cfg.hidden_size)
-        self.key_proj = nn.Linear(cfg.hidden_size, cfg.hidden_size)
-        self.value_proj = nn.Linear(cfg.hidden_size, cfg.hidden_size)
+        self.query_proj = Linear(cfg.hidden_size, cfg.hidden_size)
+        self.key_proj = Linear(cfg.hidden_size, cfg.hidden_size)
+        self.value_proj = Linear(cfg.hidden_size, cfg.hidden_size)
         self.span = cfg.position_buckets
         self.scale_factor = 3          # content + c2p + p2c
 
@@ -126,8 +129,9 @@ class DisentangledSelfAttention(nn.Module):
         v = self.value_proj(x).view(T, self.h, self.dh)
         pos_k = self.key_proj(rel_emb).view(-1, self.h, self.dh).transpose(0, 1)          # [H, NB, dh]
         pos_q = self.query_proj(rel_emb).view(-1, self.h, self.dh).transpose(0, 1)
-        rel_a = torch.bmm(q.transpose(0, 1), pos_k.transpose(1, 2)).contiguous()            # [H, T, NB]
-        rel_b = torch.bmm(k.transpose(0, 1), pos_q.transpose(1, 2)).contiguous()
+        # the two bias tables A = Qc Kr^T and B = Kc Qr^T ([H, T, NB]): per head a [T, 64] x [NB, 64]^T product on the general
+        # tcgen05 GEMM; the per-head operands are column slices of the packed projections (no copies)
+        rel_a, rel_b = _bias_tables(q, pos_k), _bias_tables(k, pos_q)
         scale = 1.0 / math.sqrt(self.dh * self.scale_factor)
         native._count()
         if os.environ.get("NANORLHF_DEBERTA_TMA", "1") != "0" and self.dh == 64:
@@ -136,6 +140,20 @@ class DisentangledSelfAttention(nn.Module):
         else:
             out, _ = native.ext().attn_varlen_fwd(q, k, v, cu_seqlens, int(max_len), scale, False, rel_a, rel_b, lut)
         return out.reshape(T, -1)
+
+
+def _bias_tables(x: torch.Tensor, pos: torch.Tensor) -> torch.Tensor:
+    """x: [T, H, dh] (a view of a packed projection), pos: [H, NB, dh] (a transposed view) -> [H, T, NB] with
+    out[h] = x[:, h] pos[h]^T."""
+    T, H, dh = x.shape
+    NB = pos.shape[1]
+    if x.is_cuda and x.dtype == torch.bfloat16 and ops.use_native(x) and dh % 8 == 0 and NB % 8 == 0:
+        from ..ops import linear as _lin
+        out = torch.empty(H, T, NB, dtype=x.dtype, device=x.device)
+        for h in range(H):
+            _lin.gemm(x[:, h], pos[h], out=out[h])
+        return out
+    return torch.bmm(x.transpose(0, 1), pos.transpose(1, 2)).contiguous()
 
 
 def build_bucket_lut(max_len: int, bucket_size: int, max_position: int, span: int, device) -> torch.Tensor:
@@ -163,7 +181,7 @@ def _add_layernorm(ln: nn.LayerNorm, y: torch.Tensor, residual: torch.Tensor) ->
 class _SelfOutput(nn.Module):
     def __init__(self, cfg):
         super().__init__()
-        self.dense = nn.Linear(cfg.hidden_size, cfg.hidden_size)
+        self.dense = Linear(cfg.hidden_size, cfg.hidden_size)
         self.LayerNorm = nn.LayerNorm(cfg.hidden_size, cfg.layer_norm_eps)
 
     def forward(self, h, residual):
@@ -183,22 +201,21 @@ class _Attention(nn.Module):
 class _Intermediate(nn.Module):
     def __init__(self, cfg):
         super().__init__()
-        self.dense = nn.Linear(cfg.hidden_size, cfg.intermediate_size)
+        self.dense = Linear(cfg.hidden_size, cfg.intermediate_size)
 
     def forward(self, x):
         # GEMM + bias + GELU epilogue (tcgen05 kernel, act=1).  Measured on B200 at 26.5k x 4096 x 1024 the erf in the
         # epilogue makes the tile epilogue longer than its 16 k-block main loop (0.41 ms vs cuBLAS 0.16 + GELU 0.12),
         # so it is opt-in until the epilogue is split across more warps.
         if _fused_inference(x) and x.shape[-1] % 8 == 0 and os.environ.get("NANORLHF_DEBERTA_GELU_FUSED", "0") == "1":
-            from ..ops import native
-            return native.gemm_bf16(x.contiguous(), self.dense.weight, self.dense.bias, act=1)
+            return ops.linear(x, self.dense.weight, self.dense.bias, act=1)
         return F.gelu(self.dense(x))
 
 
 class _Output(nn.Module):
     def __init__(self, cfg):
         super().__init__()
-        self.dense = nn.Linear(cfg.intermediate_size, cfg.hidden_size)
+        self.dense = Linear(cfg.intermediate_size, cfg.hidden_size)
         self.LayerNorm = nn.LayerNorm(cfg.hidden_size, cfg.layer_norm_eps)
 
     def forward(self, h, residual):
@@ -259,7 +276,7 @@ class _Backbone(nn.Module):
 class _Pooler(nn.Module):
     def __init__(self, cfg):
         super().__init__()
-        self.dense = nn.Linear(cfg.hidden_size, cfg.pooler_hidden_size)
+        self.dense = Linear(cfg.hidden_size, cfg.pooler_hidden_size)
 
     def forward(self, h):
         return F.gelu(self.dense(h[:, 0]))
@@ -271,7 +288,7 @@ class DebertaV3ForSequenceClassification(nn.Module):
         self.config = cfg
         self.deberta = _Backbone(cfg)
         self.pooler = _Pooler(cfg)
-        self.classifier = nn.Linear(cfg.pooler_hidden_size, cfg.num_labels)
+        self.classifier = Linear(cfg.pooler_hidden_size, cfg.num_labels)
 
     @property
     def device(self):

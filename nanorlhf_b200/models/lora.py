@@ -25,6 +25,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .. import ops
+
 DEFAULT_TARGETS = ["q_proj", "k_proj", "v_proj", "o_proj", "gate_proj", "up_proj", "down_proj"]
 
 
@@ -43,38 +45,6 @@ class LoraConfig:
     @property
     def scaling(self) -> float:
         return self.lora_alpha / self.r
-
-
-class _LoraLinearFn(torch.autograd.Function):
-    """y = x W^T + b + s (x A^T) B^T with the rank-r update folded into the base GEMM's output
-    (``addmm_`` with beta = 1): no [T, N] intermediates for the adapter branch, no separate scale / add
-    kernels, and autograd keeps only x and the [T, r] projection.  The base weight is frozen."""
-
-    @staticmethod
-    def forward(ctx, x, w, bias, a, b, scaling):
-        x2 = x.reshape(-1, x.shape[-1])
-        t = x2 @ a.t()
-        y = torch.addmm(bias, x2, w.t()) if bias is not None else x2 @ w.t()
-        y.addmm_(t, b.t(), alpha=scaling)
-        ctx.save_for_backward(x2, w, a, b, t)
-        ctx.scaling = scaling
-        ctx.xshape = x.shape
-        return y.view(*x.shape[:-1], w.shape[0])
-
-    @staticmethod
-    def backward(ctx, gy):
-        x2, w, a, b, t = ctx.saved_tensors
-        s = ctx.scaling
-        g = gy.reshape(-1, gy.shape[-1])
-        gt = g @ b                                    # [T, r]
-        gx = None
-        if ctx.needs_input_grad[0]:
-            gx = g @ w
-            gx.addmm_(gt, a, alpha=s)
-            gx = gx.view(ctx.xshape)
-        ga = (gt.t() @ x2) * s if ctx.needs_input_grad[3] else None
-        gb = (g.t() @ t) * s if ctx.needs_input_grad[4] else None
-        return gx, None, None, ga, gb, None
 
 
 class LoraLinear(nn.Module):
@@ -112,8 +82,9 @@ class LoraLinear(nn.Module):
 
     def forward(self, x):
         if isinstance(self.lora_dropout, nn.Identity) and not self.base_layer.weight.requires_grad:
-            return _LoraLinearFn.apply(x, self.base_layer.weight, self.base_layer.bias, self.lora_A.weight,
-                                       self.lora_B.weight, self.scaling)
+            # one dual-source-K tcgen05 GEMM per direction on CUDA (ops/linear.py); PyTorch oracle elsewhere
+            return ops.lora_linear(x, self.base_layer.weight, self.base_layer.bias, self.lora_A.weight,
+                                   self.lora_B.weight, self.scaling)
         y = self.base_layer(x)
         return y + self.lora_B(self.lora_A(self.lora_dropout(x))) * self.scaling
 

@@ -94,6 +94,14 @@ class Qwen2Config:
             return cls.from_dict(json.load(f))
 
 
+class Linear(nn.Linear):
+    """``nn.Linear`` (same parameters, same checkpoint names) whose three contractions -- forward, dgrad, wgrad -- run on
+    the general tcgen05 GEMM (ops/linear.py) instead of cuBLAS."""
+
+    def forward(self, x):
+        return ops.linear(x, self.weight, self.bias)
+
+
 class RMSNorm(nn.Module):
     def __init__(self, dim, eps):
         super().__init__()
@@ -109,10 +117,10 @@ class Qwen2Attention(nn.Module):
         super().__init__()
         self.cfg = cfg
         d, hd = cfg.hidden_size, cfg.head_dim
-        self.q_proj = nn.Linear(d, cfg.num_attention_heads * hd, bias=cfg.attention_bias)
-        self.k_proj = nn.Linear(d, cfg.num_key_value_heads * hd, bias=cfg.attention_bias)
-        self.v_proj = nn.Linear(d, cfg.num_key_value_heads * hd, bias=cfg.attention_bias)
-        self.o_proj = nn.Linear(cfg.num_attention_heads * hd, d, bias=False)
+        self.q_proj = Linear(d, cfg.num_attention_heads * hd, bias=cfg.attention_bias)
+        self.k_proj = Linear(d, cfg.num_key_value_heads * hd, bias=cfg.attention_bias)
+        self.v_proj = Linear(d, cfg.num_key_value_heads * hd, bias=cfg.attention_bias)
+        self.o_proj = Linear(cfg.num_attention_heads * hd, d, bias=False)
 
     def forward(self, x, cos, sin, cu_seqlens, max_seqlen):
         cfg = self.cfg
@@ -129,9 +137,9 @@ class Qwen2Attention(nn.Module):
 class Qwen2MLP(nn.Module):
     def __init__(self, cfg: Qwen2Config):
         super().__init__()
-        self.gate_proj = nn.Linear(cfg.hidden_size, cfg.intermediate_size, bias=False)
-        self.up_proj = nn.Linear(cfg.hidden_size, cfg.intermediate_size, bias=False)
-        self.down_proj = nn.Linear(cfg.intermediate_size, cfg.hidden_size, bias=False)
+        self.gate_proj = Linear(cfg.hidden_size, cfg.intermediate_size, bias=False)
+        self.up_proj = Linear(cfg.hidden_size, cfg.intermediate_size, bias=False)
+        self.down_proj = Linear(cfg.intermediate_size, cfg.hidden_size, bias=False)
 
     def forward(self, x):
         return self.down_proj(ops.swiglu_pair(self.gate_proj(x), self.up_proj(x)))
@@ -261,7 +269,7 @@ class Qwen2ForCausalLM(Qwen2PreTrained):
     def __init__(self, cfg: Qwen2Config):
         super().__init__(cfg)
         self.model = Qwen2Model(cfg)
-        self.lm_head = nn.Linear(cfg.hidden_size, cfg.vocab_size, bias=False)
+        self.lm_head = Linear(cfg.hidden_size, cfg.vocab_size, bias=False)
         self.tie_weights()
 
     def tie_weights(self):

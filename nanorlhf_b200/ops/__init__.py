@@ -80,6 +80,26 @@ def swiglu_pair(gate, up):
     return (torch.nn.functional.silu(gate.float()) * up.float()).to(gate.dtype)
 
 
+def linear(x, weight, bias=None, act: int = 0):
+    """``F.linear`` (+ optional fused exact GELU, ``act=1``) -- the general tcgen05 GEMM on CUDA bf16 (ops/linear.py)."""
+    if use_native(x):
+        _nat()
+        from . import linear as _lin
+        return _lin.linear(x, weight, bias, act)
+    y = torch.nn.functional.linear(x, weight, bias)
+    return torch.nn.functional.gelu(y) if act == 1 else y
+
+
+def lora_linear(x, weight, bias, lora_a, lora_b, scaling: float):
+    """``x W^T + b + scaling * (x A^T) B^T`` with a frozen ``W``; one dual-source-K GEMM per direction on CUDA bf16."""
+    if use_native(x):
+        _nat()
+        from . import linear as _lin
+        if _lin.lora_supported(x, weight, lora_a, lora_b):
+            return _lin.lora_linear(x, weight, bias, lora_a, lora_b, scaling)
+    return ref.lora_linear(x, weight, bias, lora_a, lora_b, scaling)
+
+
 def attention_varlen(q, k, v, cu_seqlens, max_seqlen=None, causal=True, scale=None):
     if use_native(q):
         return _nat().attention_varlen(q, k, v, cu_seqlens, max_seqlen, causal, scale)

@@ -55,35 +55,10 @@ def gemm_bf16(a, b, bias=None, out=None, block_n: int = 0, act: int = 0):
     return ext().gemm_bf16(a, b, bias, out, block_n, act)
 
 
-class _LinearFn(torch.autograd.Function):
-    """y = x W^T + b with all three GEMMs (fwd, dgrad, wgrad) on the tcgen05 kernel."""
-
-    @staticmethod
-    def forward(ctx, x, w, b):
-        x2 = x.reshape(-1, x.shape[-1])
-        y = gemm_bf16(x2.contiguous(), w, b)
-        ctx.save_for_backward(x2, w)
-        ctx.has_bias = b is not None
-        ctx.xshape = x.shape
-        return y.view(*x.shape[:-1], w.shape[0])
-
-    @staticmethod
-    def backward(ctx, gy):
-        x2, w = ctx.saved_tensors
-        g2 = gy.reshape(-1, gy.shape[-1]).contiguous()
-        gx = gw = gb = None
-        if ctx.needs_input_grad[0]:
-            # gx[M,K] = g[M,N] @ W[N,K]  ==  g @ (W^T)^T : B operand must be [K,N] K-major -> W^T contiguous
-            gx = gemm_bf16(g2, w.t().contiguous()).view(ctx.xshape)
-        if ctx.needs_input_grad[1]:
-            gw = gemm_bf16(g2.t().contiguous(), x2.t().contiguous())
-        if ctx.has_bias and ctx.needs_input_grad[2]:
-            gb = g2.sum(0)
-        return gx, gw, gb
-
-
-def linear(x, w, b=None):
-    return _LinearFn.apply(x, w, b)
+def linear(x, w, b=None, act: int = 0):
+    """y = x W^T + b with forward / dgrad / wgrad on the general tcgen05 GEMM (ops/linear.py)."""
+    from . import linear as _lin
+    return _lin.linear(x, w, b, act)
 
 
 # --------------------------------------------------------------------------------------------
@@ -204,8 +179,9 @@ def attention_varlen(q, k, v, cu_seqlens, max_seqlen=None, causal=True, scale=No
 # --------------------------------------------------------------------------------------------
 class _LmHeadLogprobFn(torch.autograd.Function):
     """Forward: tcgen05 GEMM with an online-softmax epilogue (no [T,V] tensor).
-    Backward: the same mainloop recomputes the logits and its epilogue emits dZ in bf16; the two
-    remaining products dH = dZ W and dW = dZ^T H are plain GEMMs."""
+    Backward: the same mainloop recomputes the logits and its epilogue emits dZ in bf16 (one 8192-row chunk at a
+    time); dH = dZ W (K-major x MN-major) and dW += dZ^T H (MN-major x MN-major, fp32 accumulate across chunks in the
+    epilogue) run on the general tcgen05 GEMM -- W and H are consumed as stored, nothing is transposed."""
 
     CHUNK = 8192      # rows of dZ materialised at a time in backward (8192 x 152k bf16 = 2.5 GB)
 
@@ -229,14 +205,15 @@ class _LmHeadLogprobFn(torch.autograd.Function):
         dh = torch.empty_like(h) if need_h else None
         dw = torch.zeros(weight.shape, dtype=torch.float32, device=weight.device) if need_w else None
         T = h.shape[0]
+        from . import linear as _lin
         for s in range(0, T, _LmHeadLogprobFn.CHUNK):
             e = min(T, s + _LmHeadLogprobFn.CHUNK)
             _count()
             dz = ext().lmhead_dlogits(h[s:e], weight, t32[s:e], lse[s:e], g[s:e], inv_t)
             if need_h:
-                torch.matmul(dz, weight, out=dh[s:e])
+                _lin.gemm(dz, weight, b_mn=True, out=dh[s:e])
             if need_w:
-                dw.add_(torch.matmul(dz.t(), h[s:e]))
+                _lin.gemm(dz, h[s:e], a_mn=True, b_mn=True, out_f32=dw, accumulate=True)
         return dh, (dw.to(weight.dtype) if need_w else None), None, None, None
 
 

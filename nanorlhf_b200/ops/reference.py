@@ -296,3 +296,38 @@ def top_p_sample(logits: torch.Tensor, temperature: float, top_p: float,
         choice = torch.multinomial(sp, 1, generator=generator)
         return si.gather(1, choice).squeeze(1)
     return torch.multinomial(probs, 1, generator=generator).squeeze(1)
+
+
+class _LoraLinearRef(torch.autograd.Function):
+    """PyTorch oracle / CPU backend of ``ops.lora_linear``: the rank-r update folded into the base GEMM's output
+    (``addmm_`` with beta = 1), autograd keeps only x and the [T, r] projection; the base weight is frozen."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, a, b, scaling):
+        x2 = x.reshape(-1, x.shape[-1])
+        t = x2 @ a.t()
+        y = torch.addmm(bias, x2, w.t()) if bias is not None else x2 @ w.t()
+        y.addmm_(t, b.t(), alpha=scaling)
+        ctx.save_for_backward(x2, w, a, b, t)
+        ctx.scaling = scaling
+        ctx.xshape = x.shape
+        return y.view(*x.shape[:-1], w.shape[0])
+
+    @staticmethod
+    def backward(ctx, gy):
+        x2, w, a, b, t = ctx.saved_tensors
+        s = ctx.scaling
+        g = gy.reshape(-1, gy.shape[-1])
+        gt = g @ b                                    # [T, r]
+        gx = None
+        if ctx.needs_input_grad[0]:
+            gx = g @ w
+            gx.addmm_(gt, a, alpha=s)
+            gx = gx.view(ctx.xshape)
+        ga = (gt.t() @ x2) * s if ctx.needs_input_grad[3] else None
+        gb = (g.t() @ t) * s if ctx.needs_input_grad[4] else None
+        return gx, None, None, ga, gb, None
+
+
+def lora_linear(x, w, bias, a, b, scaling: float):
+    return _LoraLinearRef.apply(x, w, bias, a, b, scaling)

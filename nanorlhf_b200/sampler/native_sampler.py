@@ -64,7 +64,9 @@ class NativeSampler:
         self.v_cache: List[torch.Tensor] = []
         self.num_blocks = 0
         self._graphs: Dict[int, tuple] = {}
-        self.stats = {"decode_steps": 0, "decode_tokens": 0, "prefill_tokens": 0, "graph_replays": 0}
+        self._state_pool: Dict[tuple, dict] = {}
+        self.stats = {"decode_steps": 0, "decode_tokens": 0, "prefill_tokens": 0, "graph_replays": 0, "compactions": 0,
+                      "row_steps": 0}
         self._build_arena()
 
     # ------------------------------------------------------------------------------------------
@@ -132,9 +134,9 @@ class NativeSampler:
         if self.num_blocks >= blocks_needed:
             return
         per_block = 2 * cfg.num_hidden_layers * cfg.num_key_value_heads * self.PAGE * cfg.head_dim * (1 if self.kv_dtype == "fp8" else 2)
-        self.k_cache, self.v_cache = [], []
+        self.k_cache, self.v_cache = [], []          # the old pool is dropped first so the allocator can reuse it
         self._graphs.clear()
-        torch.cuda.empty_cache() if self.num_blocks else None
+        self._state_pool.clear()
         free, _total = torch.cuda.mem_get_info(self.device)
         budget = int(free * self.kv_memory_fraction) if self.kv_cache_gb is None else int(self.kv_cache_gb * 2**30)
         can = budget // per_block
@@ -266,16 +268,33 @@ class NativeSampler:
     # decode
     # ------------------------------------------------------------------------------------------
     def _alloc_state(self, S: int, max_blocks: int, max_tokens: int, pad_id: int = 0):
+        """Batch state of ``S`` rows.  States are pooled per shape: the decode CUDA graph of a bucket is captured
+        against these exact tensors, so a batch that shrinks (compaction) or grows (admission) back into a bucket it
+        has used before replays the existing graph instead of capturing a new one."""
         dev = self.device
-        i32 = dict(dtype=torch.int32, device=dev)
-        return {
-            "S": S, "tokens": torch.zeros(S, **i32), "positions": torch.zeros(S, **i32),
-            "ctx_lens": torch.ones(S, **i32), "block_tables": torch.zeros(S, max_blocks, **i32),
-            "slot": torch.zeros(S, **i32), "finished": torch.ones(S, dtype=torch.bool, device=dev),
-            "gen_count": torch.zeros(S, **i32), "row_ids": torch.zeros(S, **i32),
-            "out": torch.full((S, max_tokens + 1), pad_id, dtype=torch.int32, device=dev),
-            "rows": torch.arange(S, device=dev), "splits": 1,
-        }
+        key = (S, max_blocks, max_tokens)
+        st = self._state_pool.get(key)
+        if st is None:
+            i32 = dict(dtype=torch.int32, device=dev)
+            st = {
+                "S": S, "tokens": torch.zeros(S, **i32), "positions": torch.zeros(S, **i32),
+                "ctx_lens": torch.ones(S, **i32), "block_tables": torch.zeros(S, max_blocks, **i32),
+                "slot": torch.zeros(S, **i32), "finished": torch.ones(S, dtype=torch.bool, device=dev),
+                "gen_count": torch.zeros(S, **i32), "row_ids": torch.zeros(S, **i32),
+                "out": torch.full((S, max_tokens + 1), pad_id, dtype=torch.int32, device=dev),
+                "rows": torch.arange(S, device=dev), "splits": 1,
+            }
+            if len(self._state_pool) >= 8:
+                old = next(iter(self._state_pool))
+                self._state_pool.pop(old)
+                self._graphs = {k: v for k, v in self._graphs.items() if v[1] is not None and (k[0], k[1], k[7]) != old}
+            self._state_pool[key] = st
+        else:
+            for k, fill in (("tokens", 0), ("positions", 0), ("ctx_lens", 1), ("slot", 0), ("gen_count", 0), ("row_ids", 0)):
+                st[k].fill_(fill)
+            st["finished"].fill_(True)
+            st["out"].fill_(pad_id)
+        return st
 
     def _decode_step(self, st, temperature, top_p, seed, eos_id, pad_id, max_tokens):
         """One token for every row of the batch; pure device work (graph-capturable)."""
@@ -368,9 +387,11 @@ class NativeSampler:
         scratch_block = self.num_blocks - 1
         running: List[int] = []          # seq ids in batch-row order
         st = None
+        compact = False
         while True:
             admitted = sched.admit()
-            if admitted:
+            if admitted or compact:
+                compact = False
                 # ---- prefill the newly admitted groups in token-budget chunks ----
                 new_seq, first_tok_logits_rows, chunk, tok_count = [], [], [], 0
                 logits_parts = []
@@ -390,10 +411,16 @@ class NativeSampler:
                     sched.finish([running[i] for i, f in enumerate(fin) if f])
                 new_running = [running[i] for i in keep_rows]
                 old_state = st
+                old_keep = {k: old_state[k][torch.tensor(keep_rows, device=dev)] for k in
+                            ("tokens", "positions", "ctx_lens", "finished", "gen_count", "out")} if keep_rows else None
                 for groups, _ in logits_parts:
                     for g in groups:
                         new_running += sched.group_seqs(g)
                 S_real = len(new_running)
+                if S_real == 0:
+                    if sched.num_waiting() > 0:
+                        raise RuntimeError("KV pool too small: a waiting request group cannot be admitted into an empty batch")
+                    break
                 S = max(128, (S_real + 127) // 128 * 128) if self.use_cuda_graph else S_real
                 st = self._alloc_state(S, per_seq_blocks, max_tokens, pad_id)
                 st["block_tables"].fill_(scratch_block)
@@ -404,10 +431,9 @@ class NativeSampler:
                 st["block_tables"][:S_real].copy_(bt.to(dev))
                 st["row_ids"][:S_real].copy_(torch.tensor(new_running, dtype=torch.int32))
                 nk = len(keep_rows)
-                if nk:
-                    idx = torch.tensor(keep_rows, device=dev)
-                    for k in ("tokens", "positions", "ctx_lens", "finished", "gen_count", "out"):
-                        st[k][:nk].copy_(old_state[k][idx])
+                if nk:                               # (gathered before the pooled state was reset: it may be the same tensors)
+                    for k, v in old_keep.items():
+                        st[k][:nk].copy_(v)
                 # first token of every new sequence: sample from the prompt's last-position logits
                 r0 = nk
                 for groups, logits in logits_parts:
@@ -436,17 +462,25 @@ class NativeSampler:
             # ---- decode until the next sync point ----
             self._run_decode(st, self.sync_every, temperature, top_p, seed, eos_id, pad_id, max_tokens)
             self.stats["decode_steps"] += self.sync_every
+            self.stats["row_steps"] += self.sync_every * st["S"]
             fin = st["finished"][:len(running)]
             n_fin = int(fin.sum().item())                     # the only host sync of the decode loop
             if n_fin == len(running) and sched.num_waiting() == 0:
                 self._flush_rows(st, running, out, max_tokens, n)
                 sched.finish(running)
                 break
-            if sched.num_waiting() > 0 and n_fin > 0:
-                # release pages of finished rows so `admit` can bring waiting groups in
-                done_rows = fin.nonzero().squeeze(1).tolist()
-                self._flush_rows(st, running, out, max_tokens, n)
-                sched.finish([running[i] for i in done_rows])
+            if n_fin > 0:
+                # Finished rows still cost a GEMM row and a (short) KV read every step.  Release their pages and
+                # rebuild the batch without them when that lets a waiting group in, or when the survivors fit a
+                # smaller graph bucket (the reference's vLLM does the same every step; here every sync point).
+                live = len(running) - n_fin
+                bucket = max(128, (live + 127) // 128 * 128) if self.use_cuda_graph else live
+                if sched.num_waiting() > 0 or bucket < st["S"]:
+                    done_rows = fin.nonzero().squeeze(1).tolist()
+                    self._flush_rows(st, running, out, max_tokens, n)
+                    sched.finish([running[i] for i in done_rows])
+                    compact = True
+                    self.stats["compactions"] += 1
         self.stats["decode_tokens"] += int((out != pad_id).sum().item())
         self.lm.train(was_training)
         return out
