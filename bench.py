@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--model", default="1.5b", choices=["tiny", "1.5b", "7b"])
     ap.add_argument("--comm", default="fused", choices=["fused", "nccl"])
     ap.add_argument("--rollout-dtype", default="bf16")
+    ap.add_argument("--kv-dtype", default="bf16", choices=["bf16", "fp8"], help="sampler KV pages (fp8 = e4m3 + per-token scales)")
     ap.add_argument("--reward", default="deberta-large", choices=["deberta-large", "deberta-tiny"])
     ap.add_argument("--grad-checkpointing", type=int, default=0,
                     help="1 = recompute activations like the reference (A100-40G memory saver); 0 = keep them (B200: 180 GB)")
@@ -122,7 +123,7 @@ def main():
                      num_mini_batches=args.mini_batches, num_ppo_epochs=1,
                      total_episodes=prompts_per_rank * comm.world_size * total_updates, learning_rate=6e-6,
                      gradient_checkpointing=bool(args.grad_checkpointing), save_strategy="no", report_to="none", sampler="native",
-                     rollout_dtype=args.rollout_dtype, comm=args.comm, resume="never", grpo_sample_N=args.samples,
+                     rollout_dtype=args.rollout_dtype, kv_cache_dtype=args.kv_dtype, comm=args.comm, resume="never", grpo_sample_N=args.samples,
                      watchdog_timeout_s=0)
     cfg.quiet = True
     dataset = synthetic_token_dataset(prompts_per_rank * comm.world_size * 2, shape.vocab_size - 2, 24, 160, seed=1)
@@ -189,7 +190,7 @@ def main():
                        "global_batch": prompts_per_rank * comm.world_size, "prompts_per_rank": prompts_per_rank,
                        "sequences_per_rank": prompts_per_rank * args.samples, "samples_per_prompt": args.samples,
                        "seq_len": args.response_length, "prompt_len": "24-160", "parallelism": f"dp{comm.world_size}",
-                       "comm": args.comm if comm.world_size > 1 else "none", "rollout_dtype": args.rollout_dtype,
+                       "comm": args.comm if comm.world_size > 1 else "none", "rollout_dtype": args.rollout_dtype, "kv_cache_dtype": args.kv_dtype,
                        "gradient_checkpointing": bool(args.grad_checkpointing),
                        "l2_policy": "working set (3 GB weights + KV pages + activations) exceeds the 126 MB L2 every step"},
             "e2e": {"value": e2e, "unit": "episodes/s", "h2d_bytes_per_step": (trainer.io_bytes["h2d"] - h2d0) / args.steps,

@@ -37,7 +37,8 @@ policy = get_peft_model(Qwen2ForCausalLM.from_config(shape, torch.bfloat16, dev,
 
 if "decode" in which:
     S, ctx, max_tokens = int(os.environ.get("S", "2048")), int(os.environ.get("CTX", "1000")), 16
-    eng = NativeSampler(policy, use_cuda_graph=False, rollout_dtype=os.environ.get("ROLLOUT", "bf16"))
+    eng = NativeSampler(policy, use_cuda_graph=False, rollout_dtype=os.environ.get("ROLLOUT", "bf16"),
+                        kv_cache_dtype=os.environ.get("KV", "bf16"))
     eng.sync_weights()
     per = (ctx + max_tokens) // 16 + 2
     eng._ensure_kv(S * per + 8)
@@ -54,7 +55,7 @@ if "decode" in which:
         for _ in range(4):
             eng._decode_step(st, 0.9, 0.95, 1, None, shape.vocab_size - 1, 10**6)
         torch.cuda.synchronize()
-    table(prof, f"decode x4 steps, S={S}, ctx={ctx}, rollout_dtype={os.environ.get('ROLLOUT', 'bf16')}")
+    table(prof, f"decode x4 steps, S={S}, ctx={ctx}, rollout_dtype={os.environ.get('ROLLOUT', 'bf16')}, kv={os.environ.get('KV', 'bf16')}")
     del eng, st
     torch.cuda.empty_cache()
 

@@ -113,9 +113,7 @@ TcChoice pick_tc_tile(int64_t M, int64_t N, bool a_mn, bool b_mn, bool f32_out) 
   TcChoice best{1, 128};
   double best_s = -1.0;
   for (const Cand& c : all) {
-    if (b_mn && (c.bn / c.cg) % 64 != 0) continue;                       // MN-major B tiles are made of 64-column panels
     if (a_mn && !((c.cg == 1 && c.bn != 192) || (c.cg == 2 && c.bn == 256))) continue;      // instantiated wgrad shapes
-    if (!a_mn && b_mn && c.cg == 2 && c.bn == 192) continue;
     if (f32_out && !a_mn) continue;
     const int64_t tm = c.cg * 128;
     const int64_t num_m = (M + tm - 1) / tm, num_n = (N + c.bn - 1) / c.bn, tiles = num_m * num_n;
@@ -139,7 +137,7 @@ inline void check_tc_operand(const torch::Tensor& t, const char* name) {
 torch::Tensor gemm_tc(const torch::Tensor& a, const torch::Tensor& b, bool a_mn, bool b_mn, const c10::optional<torch::Tensor>& a2,
                       const c10::optional<torch::Tensor>& b2, const c10::optional<torch::Tensor>& bias, int64_t act, double alpha,
                       c10::optional<torch::Tensor> out_opt, c10::optional<torch::Tensor> out_f32, bool accumulate, int64_t cg_req,
-                      int64_t bn_req) {
+                      int64_t bn_req, int64_t splitk_req) {
   check_tc_operand(a, "a");
   check_tc_operand(b, "b");
   const int64_t M = a_mn ? a.size(1) : a.size(0), K = a_mn ? a.size(0) : a.size(1);
@@ -170,6 +168,40 @@ torch::Tensor gemm_tc(const torch::Tensor& a, const torch::Tensor& b, bool a_mn,
     TORCH_CHECK(out.size(0) == M && out.size(1) == N, "gemm_tc: out has the wrong shape");
   }
   if (M == 0 || N == 0) return out;
+  // ---- split-K: few output tiles, long contraction (rank-r projections, LoRA weight gradients) ----
+  if (cg_req <= 0 && bn_req <= 0 && K2 == 0 && !f32 && !bias.has_value() && act == 0 && (a_mn == b_mn || !a_mn) && splitk_req != 0) {
+    const int bn = N <= 64 ? 64 : 128;
+    const int64_t tiles = ((M + 127) / 128) * ((N + bn - 1) / bn), num_kb = (K + 63) / 64;
+    const int sms = num_sms();
+    int64_t splits = splitk_req > 0 ? splitk_req : std::min<int64_t>(std::min<int64_t>(sms / std::max<int64_t>(tiles, 1), num_kb / 4), 16);
+    if (splitk_req > 0 || (tiles * 2 <= sms && N <= 128 && splits >= 2)) {
+      splits = std::max<int64_t>(1, std::min<int64_t>(splits, num_kb));
+      const int64_t per = (num_kb + splits - 1) / splits;
+      splits = (num_kb + per - 1) / per;                                 // no empty k-range
+      static thread_local torch::Tensor ws, counters;
+      const int64_t need = splits * tiles * 128 * bn;
+      if (!ws.defined() || ws.numel() < need || ws.device() != a.device())
+        ws = torch::empty({std::max<int64_t>(need, 1 << 22)}, a.options().dtype(torch::kFloat32));
+      if (!counters.defined() || counters.numel() < tiles || counters.device() != a.device())
+        counters = torch::zeros({std::max<int64_t>(tiles, 4096)}, a.options().dtype(torch::kInt32));
+      const auto BF = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+      CUtensorMap maps2[2];
+      maps2[0] = a_mn ? nrl::make_tma_2d(a.data_ptr(), a.size(0), a.size(1), a.stride(0) * 2, 64, 64, BF, 2)
+                      : nrl::make_tma_2d(a.data_ptr(), a.size(0), a.size(1), a.stride(0) * 2, 128, 64, BF, 2);
+      maps2[1] = b_mn ? nrl::make_tma_2d(b.data_ptr(), b.size(0), b.size(1), b.stride(0) * 2, 64, 64, BF, 2)
+                      : nrl::make_tma_2d(b.data_ptr(), b.size(0), b.size(1), b.stride(0) * 2, bn, 64, BF, 2);
+      nrl::tc::TcParams ps{};
+      ps.M = static_cast<int>(M); ps.N = static_cast<int>(N); ps.K = static_cast<int>(K); ps.K2 = 0;
+      ps.alpha = static_cast<float>(alpha);
+      ps.splits = static_cast<int>(splits);
+      ps.ws = ws.data_ptr<float>();
+      ps.counters = counters.data_ptr<int>();
+      ps.out_bf16 = reinterpret_cast<__nv_bfloat16*>(out.data_ptr());
+      ps.out_stride = out.stride(0);
+      check(nrl_gemm_tc_splitk(maps2, &ps, bn, a_mn ? 1 : 0, b_mn ? 1 : 0, sms, cur_stream()), "gemm_tc_splitk");
+      return out;
+    }
+  }
   TcChoice ch = pick_tc_tile(M, N, a_mn, b_mn, f32);
   if (cg_req > 0) ch.cg = static_cast<int>(cg_req);
   if (bn_req > 0) ch.bn = static_cast<int>(bn_req);
@@ -204,6 +236,67 @@ torch::Tensor gemm_tc(const torch::Tensor& a, const torch::Tensor& b, bool a_mn,
   }
   check(nrl_gemm_tc(maps, &p, ch.cg, ch.bn, a_mn ? 1 : 0, b_mn ? 1 : 0, f32 ? nrl::tc::EPI_F32 : nrl::tc::EPI_BF16, num_sms(),
                     cur_stream()), "gemm_tc (no kernel instantiated for this cg / block_n / operand-major combination?)");
+  return out;
+}
+
+// out[b] = a[b] . b[b]^T for b < B: a [B, M, K], b [B, N, K], out [B, M, N]; any batch / row strides (inner stride 1), e.g. the
+// per-head slices of packed [T, H, d] projections (DeBERTa bias tables) -- one launch, 3D TMA, no per-head copies.
+torch::Tensor gemm_tc_batched(const torch::Tensor& a, const torch::Tensor& b, c10::optional<torch::Tensor> out_opt, int64_t cg_req, int64_t bn_req) {
+  auto chk = [](const torch::Tensor& t, const char* name) {
+    TORCH_CHECK(t.is_cuda() && t.scalar_type() == torch::kBFloat16 && t.dim() == 3 && t.stride(2) == 1 && (t.stride(1) * 2) % 16 == 0 &&
+                (t.stride(0) * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(t.data_ptr()) & 15) == 0, name,
+                " must be a 3D CUDA bf16 tensor with unit inner stride and 16-byte aligned row / batch strides");
+  };
+  chk(a, "a");
+  chk(b, "b");
+  const int64_t B = a.size(0), M = a.size(1), K = a.size(2), N = b.size(1);
+  TORCH_CHECK(b.size(0) == B && b.size(2) == K && N % 8 == 0, "gemm_tc_batched: shapes differ");
+  c10::cuda::CUDAGuard guard(a.device());
+  torch::Tensor out = out_opt.has_value() ? *out_opt : torch::empty({B, M, N}, a.options());
+  chk(out, "out");
+  TORCH_CHECK(out.size(0) == B && out.size(1) == M && out.size(2) == N, "gemm_tc_batched: out has the wrong shape");
+  if (B == 0 || M == 0) return out;
+  TcChoice ch = pick_tc_tile(M * B, N, false, false, false);
+  if (ch.bn == 192 || ch.bn == 64) ch.bn = N > 128 ? 256 : 128;
+  if (cg_req > 0) ch.cg = static_cast<int>(cg_req);
+  if (bn_req > 0) ch.bn = static_cast<int>(bn_req);
+  const auto BF = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  CUtensorMap maps[3];
+  maps[0] = nrl::make_tma_3d(a.data_ptr(), B, M, K, a.stride(1) * 2, a.stride(0) * 2, 128, 64, BF, 2);
+  maps[1] = nrl::make_tma_3d(b.data_ptr(), B, N, K, b.stride(1) * 2, b.stride(0) * 2, ch.bn / ch.cg, 64, BF, 2);
+  maps[2] = nrl::make_tma_3d(out.data_ptr(), B, M, N, out.stride(1) * 2, out.stride(0) * 2, 128, 64, BF, 2);
+  nrl::tc::TcParams p{};
+  p.M = static_cast<int>(M); p.N = static_cast<int>(N); p.K = static_cast<int>(K); p.alpha = 1.f; p.batch = static_cast<int>(B);
+  check(nrl_gemm_tc_batched(maps, &p, ch.cg, ch.bn, num_sms(), cur_stream()), "gemm_tc_batched");
+  return out;
+}
+
+// act[M, F] = silu(x Wg^T) * (x Wu^T) on gemm_tc (cta_group 1 | 2): w_interleaved [2F, K], rows per 32 features [32 gate | 32 up]
+torch::Tensor gemm_tc_swiglu(const torch::Tensor& a, const torch::Tensor& w_interleaved, c10::optional<torch::Tensor> out_opt, int64_t cg_req,
+                             int64_t bn_req) {
+  check_tc_operand(a, "a");
+  check_tc_operand(w_interleaved, "w");
+  const int64_t M = a.size(0), K = a.size(1), N2 = w_interleaved.size(0);
+  TORCH_CHECK(w_interleaved.size(1) == K && N2 % 128 == 0, "gemm_tc_swiglu: 2F must be a multiple of 128");
+  c10::cuda::CUDAGuard guard(a.device());
+  torch::Tensor out = out_opt.has_value() ? *out_opt : torch::empty({M, N2 / 2}, a.options());
+  check_tc_operand(out, "out");
+  if (M == 0) return out;
+  TcChoice ch = pick_tc_tile(M, N2, false, false, false);
+  if (ch.bn == 192 || ch.bn == 64) ch.bn = (N2 % 256 == 0) ? 256 : 128;         // instantiated SwiGLU tiles
+  if (N2 % ch.bn != 0) ch.bn = 128;
+  if (cg_req > 0) ch.cg = static_cast<int>(cg_req);
+  if (bn_req > 0) ch.bn = static_cast<int>(bn_req);
+  const auto BF = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  CUtensorMap maps[5];
+  maps[0] = nrl::make_tma_2d(a.data_ptr(), M, K, a.stride(0) * 2, 128, 64, BF, 2);
+  maps[1] = nrl::make_tma_2d(w_interleaved.data_ptr(), N2, K, w_interleaved.stride(0) * 2, ch.bn / ch.cg, 64, BF, 2);
+  maps[2] = maps[0];
+  maps[3] = maps[1];
+  maps[4] = nrl::make_tma_2d(out.data_ptr(), M, N2 / 2, out.stride(0) * 2, 128, 64, BF, 2);
+  nrl::tc::TcParams p{};
+  p.M = static_cast<int>(M); p.N = static_cast<int>(N2); p.K = static_cast<int>(K); p.alpha = 1.f;
+  check(nrl_gemm_tc(maps, &p, ch.cg, ch.bn, 0, 0, nrl::tc::EPI_SWIGLU, num_sms(), cur_stream()), "gemm_tc_swiglu");
   return out;
 }
 
@@ -832,7 +925,11 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("block_n") = 0, py::arg("act") = 0);
   m.def("gemm_tc", &gemm_tc, py::arg("a"), py::arg("b"), py::arg("a_mn") = false, py::arg("b_mn") = false, py::arg("a2") = py::none(),
         py::arg("b2") = py::none(), py::arg("bias") = py::none(), py::arg("act") = 0, py::arg("alpha") = 1.0, py::arg("out") = py::none(),
-        py::arg("out_f32") = py::none(), py::arg("accumulate") = false, py::arg("cg") = 0, py::arg("block_n") = 0);
+        py::arg("out_f32") = py::none(), py::arg("accumulate") = false, py::arg("cg") = 0, py::arg("block_n") = 0,
+        py::arg("split_k") = -1);      // -1 = automatic, 0 = never, n = exactly n k-ranges
+  m.def("gemm_tc_batched", &gemm_tc_batched, py::arg("a"), py::arg("b"), py::arg("out") = py::none(), py::arg("cg") = 0, py::arg("block_n") = 0);
+  m.def("gemm_tc_swiglu", &gemm_tc_swiglu, py::arg("a"), py::arg("w_interleaved"), py::arg("out") = py::none(), py::arg("cg") = 0,
+        py::arg("block_n") = 0);
   m.def("add_layernorm", &add_layernorm);
   m.def("lmhead_logprob_fwd", &lmhead_logprob_fwd, py::arg("hidden"), py::arg("weight"), py::arg("targets"),
         py::arg("inv_temperature"), py::arg("n_splits") = 0);

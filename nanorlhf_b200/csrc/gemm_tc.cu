@@ -43,10 +43,13 @@ constexpr int kSmemBudget = 227 * 1024;
 constexpr uint32_t kPeerMask = 0xFEFFFFFFu;         // clears the CTA-pair peer bit of a shared::cluster address
 constexpr int GROUP_M = 8;                          // tile rows per L2 super-row
 
-template <int CG, int BN>
+template <int CG, int BN, bool B_MN = false>
 struct Cfg {
-  static constexpr int kBRows = BN / CG;                                  // B rows (n) this CTA loads per k-block
-  static constexpr int kBBytes = kBRows * BLOCK_K * 2;
+  static constexpr int kBRows = BN / CG;                                  // B rows (n) this CTA contributes per k-block
+  // an MN-major B tile is made of whole [64 k x 64 n] panels: 96 columns (BN = 192 on a CTA pair) load two panels, the
+  // MMA reads the first 96 columns of them (the surplus 32 belong to the peer / the next tile and are ignored)
+  static constexpr int kBPanels = (kBRows + 63) / 64;
+  static constexpr int kBBytes = B_MN ? kBPanels * kPanelBytes : kBRows * BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStagesFit = (kSmemBudget - 2 * kStagingBytes - 1024) / kStageBytes;
   static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
@@ -147,10 +150,25 @@ NRL_DEVICE TileCoord tile_coord(int t, int num_m, int num_n) {
   return c;
 }
 
-template <int CG, int BN, bool A_MN, bool B_MN, int EPI>
+template <int CG>
+NRL_DEVICE void tma_load3_cg(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+  if (CG == 1) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+  } else {
+    asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerMask), "r"(c0), "r"(c1), "r"(c2) : "memory");
+  }
+}
+NRL_DEVICE void tma_store_3d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+template <int CG, int BN, bool A_MN, bool B_MN, int EPI, bool SPLIT = false, bool BATCH = false>
 NRL_DEVICE void gemm_tc_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmA2, const CUtensorMap& tmB2,
                              const CUtensorMap& tmD, const TcParams& p) {
-  using C = Cfg<CG, BN>;
+  using C = Cfg<CG, BN, B_MN>;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::kBarOff);      // CG = 2: the leader's are the live ones
   uint64_t* empty_bar = full_bar + C::kStages;                              // per CTA (multicast commit)
@@ -165,8 +183,13 @@ NRL_DEVICE void gemm_tc_body(const CUtensorMap& tmA, const CUtensorMap& tmB, con
   const int num_n = (p.N + BN - 1) / BN;
   const int num_kb1 = (p.K + BLOCK_K - 1) / BLOCK_K;
   const int num_kb = num_kb1 + (p.K2 + BLOCK_K - 1) / BLOCK_K;
-  const int num_work = num_m * num_n;
+  const int splits = SPLIT ? p.splits : 1;
+  const int kb_per_split = (num_kb + splits - 1) / splits;
+  const int tiles_per_batch = num_m * num_n;
+  // SPLIT: work item = (tile, k-range), splits of a tile adjacent.  BATCH: work item = (batch, tile), third TMA coordinate
+  const int num_work = tiles_per_batch * (BATCH ? p.batch : splits);
   const int unit = blockIdx.x / CG, num_units = gridDim.x / CG;
+  volatile int* s_last = reinterpret_cast<volatile int*>(tmem_ptr + 1);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -175,7 +198,7 @@ NRL_DEVICE void gemm_tc_body(const CUtensorMap& tmA, const CUtensorMap& tmB, con
       tma_prefetch_desc(&tmA2);
       tma_prefetch_desc(&tmB2);
     }
-    if (EPI == EPI_BF16) tma_prefetch_desc(&tmD);
+    if (EPI != EPI_F32) tma_prefetch_desc(&tmD);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < C::kStages; ++i) {
@@ -204,10 +227,12 @@ NRL_DEVICE void gemm_tc_body(const CUtensorMap& tmA, const CUtensorMap& tmB, con
       int stage = 0;
       uint32_t phase = 0;
       for (int w = unit; w < num_work; w += num_units) {
-        const TileCoord c = tile_coord(w, num_m, num_n);
+        const int bidx = BATCH ? w / tiles_per_batch : 0;
+        const TileCoord c = tile_coord(BATCH ? w % tiles_per_batch : w / splits, num_m, num_n);
         const int m0 = (c.m_tile * CG + static_cast<int>(rank)) * BLOCK_M;
         const int n0 = c.n_blk * BN + static_cast<int>(rank) * C::kBRows;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int kb_lo = BATCH ? 0 : (w % splits) * kb_per_split, kb_hi = BATCH ? num_kb : min(num_kb, kb_lo + kb_per_split);
+        for (int kb = kb_lo; kb < kb_hi; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::kStageBytes;
           uint8_t* sb = sa + kABytes;
@@ -216,6 +241,12 @@ NRL_DEVICE void gemm_tc_body(const CUtensorMap& tmA, const CUtensorMap& tmB, con
           const CUtensorMap* ma = second ? &tmA2 : &tmA;
           const CUtensorMap* mb = second ? &tmB2 : &tmB;
           const int k0 = (second ? kb - num_kb1 : kb) * BLOCK_K;
+          if (BATCH) {
+            tma_load3_cg<CG>(sa, ma, &full_bar[stage], k0, m0, bidx);
+            tma_load3_cg<CG>(sb, mb, &full_bar[stage], k0, n0, bidx);
+            if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+            continue;
+          }
           if (A_MN) {          // stored [K rows][M cols]: two [64 k x 64 m] panels
             tma_load_cg<CG>(sa, ma, &full_bar[stage], m0, k0);
             tma_load_cg<CG>(sa + kPanelBytes, ma, &full_bar[stage], m0 + 64, k0);
@@ -224,7 +255,7 @@ NRL_DEVICE void gemm_tc_body(const CUtensorMap& tmA, const CUtensorMap& tmB, con
           }
           if (B_MN) {
 #pragma unroll
-            for (int pn = 0; pn < C::kBRows / 64; ++pn)
+            for (int pn = 0; pn < C::kBPanels; ++pn)
               tma_load_cg<CG>(sb + pn * kPanelBytes, mb, &full_bar[stage], n0 + pn * 64, k0);
           } else {
             tma_load_cg<CG>(sb, mb, &full_bar[stage], k0, n0);
@@ -245,7 +276,8 @@ NRL_DEVICE void gemm_tc_body(const CUtensorMap& tmA, const CUtensorMap& tmB, con
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int kb_lo = BATCH ? 0 : (w % splits) * kb_per_split, kb_hi = BATCH ? num_kb : min(num_kb, kb_lo + kb_per_split);
+        for (int kb = kb_lo; kb < kb_hi; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * C::kStageBytes);
@@ -257,7 +289,7 @@ NRL_DEVICE void gemm_tc_body(const CUtensorMap& tmA, const CUtensorMap& tmB, con
                                         : make_smem_desc_sw128(a_addr + k * UMMA_K * 2);
             const uint64_t bdesc = B_MN ? make_smem_desc_sw128_mn(b_addr + k * UMMA_K * 128, kPanelBytes)
                                         : make_smem_desc_sw128(b_addr + k * UMMA_K * 2);
-            umma_bf16<CG>(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_bf16<CG>(d_tmem, adesc, bdesc, idesc, ((kb - kb_lo) | k) != 0 ? 1u : 0u);
           }
           umma_commit_cg<CG>(&empty_bar[stage]);        // smem stage reusable once these MMAs retire
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
@@ -277,13 +309,68 @@ NRL_DEVICE void gemm_tc_body(const CUtensorMap& tmA, const CUtensorMap& tmB, con
     uint8_t* staging = smem + C::kStagingOff;
     int store_buf = 0;
     for (int w = unit; w < num_work; w += num_units) {
-      const TileCoord c = tile_coord(w, num_m, num_n);
+      const int tile_id = BATCH ? w % tiles_per_batch : w / splits;
+      const int bidx = BATCH ? w / tiles_per_batch : 0;
+      (void)bidx;
+      const TileCoord c = tile_coord(tile_id, num_m, num_n);
       const int m_blk = c.m_tile * CG + static_cast<int>(rank);
       const int row = m_blk * BLOCK_M + row_in_tile;
       const bool row_ok = row < p.M;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_acc = tmem_base + acc * BN + (static_cast<uint32_t>(quad * 32) << 16);
+      uint32_t sw_packed[32];
+      (void)sw_packed;
+      if (SPLIT) {
+        // ---- split-K: park the fp32 partial tile, the last CTA of the tile reduces all partials in split order ----
+        const long tile_elems = static_cast<long>(BLOCK_M) * BN;
+        float* mine = p.ws + (static_cast<long>(w % splits) * (num_m * num_n) + tile_id) * tile_elems + static_cast<long>(row_in_tile) * BN;
+#pragma unroll 1
+        for (int ch = 0; ch < BN / 32; ++ch) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(t_acc + ch * 32, v);
+          tmem_ld_wait();
+          if (ch == BN / 32 - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+          }
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            __stcg(reinterpret_cast<float4*>(mine + ch * 32 + j),
+                   make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])));
+        }
+        __threadfence();                                   // this thread's partial is visible device-wide ...
+        named_barrier_sync(1, kEpiThreads);                // ... and so is every other epilogue thread's
+        if (epi_tid == 0) {
+          const int old = atomicAdd(p.counters + tile_id, 1);
+          const int last = (old == splits - 1) ? 1 : 0;
+          if (last) p.counters[tile_id] = 0;               // self-reset for the next launch
+          __threadfence();
+          *s_last = last;
+        }
+        named_barrier_sync(2, kEpiThreads);
+        if (*s_last && row_ok) {
+          const float* base = p.ws + static_cast<long>(tile_id) * tile_elems + static_cast<long>(row_in_tile) * BN;
+          const long split_stride = static_cast<long>(num_m * num_n) * tile_elems;
+          __nv_bfloat16* orow = p.out_bf16 + static_cast<long>(row) * p.out_stride + c.n_blk * BN;
+#pragma unroll 1
+          for (int j = 0; j < BN; j += 8) {
+            if (c.n_blk * BN + j >= p.N) break;            // N % 8 == 0
+            float s8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            for (int sp = 0; sp < splits; ++sp) {
+              const float4 x = __ldcg(reinterpret_cast<const float4*>(base + sp * split_stride + j));
+              const float4 y = __ldcg(reinterpret_cast<const float4*>(base + sp * split_stride + j + 4));
+              s8[0] += x.x; s8[1] += x.y; s8[2] += x.z; s8[3] += x.w; s8[4] += y.x; s8[5] += y.y; s8[6] += y.z; s8[7] += y.w;
+            }
+            *reinterpret_cast<uint4*>(orow + j) = make_uint4(pack_bf16x2(s8[0] * p.alpha, s8[1] * p.alpha), pack_bf16x2(s8[2] * p.alpha, s8[3] * p.alpha),
+                                                             pack_bf16x2(s8[4] * p.alpha, s8[5] * p.alpha), pack_bf16x2(s8[6] * p.alpha, s8[7] * p.alpha));
+          }
+        }
+        named_barrier_sync(1, kEpiThreads);                // s_last is rewritten by the next work item
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        continue;
+      }
 #pragma unroll 1
       for (int ch = 0; ch < BN / 64; ++ch) {
         uint32_t v[2][32];
@@ -320,6 +407,36 @@ NRL_DEVICE void gemm_tc_body(const CUtensorMap& tmA, const CUtensorMap& tmB, con
                 }
               }
           }
+        } else if (EPI == EPI_SWIGLU) {
+          // every 64-column chunk of the accumulator is [32 gate | 32 up] of the same 32 features (weight rows interleaved at
+          // weight-refresh time, parallel/weight_sync.py): silu(g) * u is formed in registers, two chunks make one 64-wide
+          // output slab -- the [tokens, 2F] gate_up tensor never exists
+          constexpr float kLog2e = 1.4426950408889634f;
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const float g0 = __uint_as_float(v[0][j]), g1 = __uint_as_float(v[0][j + 1]);
+            const float u0 = __uint_as_float(v[1][j]), u1 = __uint_as_float(v[1][j + 1]);
+            const uint32_t pk = pack_bf16x2(g0 / (1.f + exp2f(-g0 * kLog2e)) * u0, g1 / (1.f + exp2f(-g1 * kLog2e)) * u1);
+            if ((ch & 1) == 0) sw_packed[j / 2] = pk;     // static indices: the array stays in registers
+            else sw_packed[16 + j / 2] = pk;
+          }
+          if (ch & 1) {
+            uint8_t* buf = staging + store_buf * kStagingBytes;
+            if (epi_tid == 0) tma_store_wait_read<1>();
+            named_barrier_sync(1, kEpiThreads);
+            uint8_t* rowp = buf + row_in_tile * 128;
+#pragma unroll
+            for (int q8 = 0; q8 < 8; ++q8)
+              *reinterpret_cast<uint4*>(rowp + ((q8 ^ (row_in_tile & 7)) * 16)) =
+                  make_uint4(sw_packed[q8 * 4], sw_packed[q8 * 4 + 1], sw_packed[q8 * 4 + 2], sw_packed[q8 * 4 + 3]);
+            fence_proxy_async_smem();
+            named_barrier_sync(2, kEpiThreads);
+            if (epi_tid == 0) {
+              tma_store_2d(&tmD, buf, c.n_blk * (BN / 2) + (ch >> 1) * 64, m_blk * BLOCK_M);
+              tma_store_commit();
+            }
+            store_buf ^= 1;
+          }
         } else {
           uint8_t* buf = staging + store_buf * kStagingBytes;
           if (epi_tid == 0) tma_store_wait_read<1>();   // the store that last used `buf` has drained
@@ -349,7 +466,8 @@ NRL_DEVICE void gemm_tc_body(const CUtensorMap& tmA, const CUtensorMap& tmB, con
           fence_proxy_async_smem();
           named_barrier_sync(2, kEpiThreads);
           if (epi_tid == 0) {
-            tma_store_2d(&tmD, buf, col0, m_blk * BLOCK_M);
+            if (BATCH) tma_store_3d(&tmD, buf, col0, m_blk * BLOCK_M, bidx);
+            else tma_store_2d(&tmD, buf, col0, m_blk * BLOCK_M);
             tma_store_commit();
           }
           store_buf ^= 1;
@@ -357,7 +475,7 @@ NRL_DEVICE void gemm_tc_body(const CUtensorMap& tmA, const CUtensorMap& tmB, con
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-    if (EPI == EPI_BF16 && epi_tid == 0) tma_store_wait<0>();
+    if (EPI != EPI_F32 && !SPLIT && epi_tid == 0) tma_store_wait<0>();
   }
 
   tc_fence_before();
@@ -384,10 +502,72 @@ gemm_tc_cg2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   gemm_tc_body<2, BN, A_MN, B_MN, EPI>(tmA, tmB, tmA2, tmB2, tmD, p);
 }
 
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tc_batched_cg1_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                           const __grid_constant__ CUtensorMap tmD, const TcParams p) {
+  gemm_tc_body<1, BN, false, false, EPI_BF16, false, true>(tmA, tmB, tmA, tmB, tmD, p);
+}
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm_tc_batched_cg2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                           const __grid_constant__ CUtensorMap tmD, const TcParams p) {
+  gemm_tc_body<2, BN, false, false, EPI_BF16, false, true>(tmA, tmB, tmA, tmB, tmD, p);
+}
+template <int CG, int BN>
+static cudaError_t launch_batched(const CUtensorMap* maps, const TcParams& p, int num_sms, cudaStream_t stream) {
+  using C = Cfg<CG, BN, false>;
+  const int num_m = (p.M + CG * BLOCK_M - 1) / (CG * BLOCK_M), num_n = (p.N + BN - 1) / BN;
+  long units = static_cast<long>(num_m) * num_n * p.batch;
+  if (units > num_sms / CG) units = num_sms / CG;
+  if (units < 1) units = 1;
+  static bool configured = false;
+  if (CG == 1) {
+    auto kern = gemm_tc_batched_cg1_kernel<BN>;
+    if (!configured) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kTotal);
+      if (e != cudaSuccess) return e;
+      configured = true;
+    }
+    kern<<<static_cast<int>(units), kThreads, C::kTotal, stream>>>(maps[0], maps[1], maps[2], p);
+  } else {
+    auto kern = gemm_tc_batched_cg2_kernel<BN>;
+    if (!configured) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kTotal);
+      if (e != cudaSuccess) return e;
+      configured = true;
+    }
+    kern<<<static_cast<int>(2 * units), kThreads, C::kTotal, stream>>>(maps[0], maps[1], maps[2], p);
+  }
+  return cudaGetLastError();
+}
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tc_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+  gemm_tc_body<1, BN, A_MN, B_MN, EPI_BF16, true>(tmA, tmB, tmA, tmB, tmA, p);
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static cudaError_t launch_splitk(const CUtensorMap* maps, const TcParams& p, int num_sms, cudaStream_t stream) {
+  using C = Cfg<1, BN, B_MN>;
+  auto kern = gemm_tc_splitk_kernel<BN, A_MN, B_MN>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kTotal);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const int tiles = ((p.M + BLOCK_M - 1) / BLOCK_M) * ((p.N + BN - 1) / BN);
+  int grid = tiles * p.splits;
+  if (grid > num_sms) grid = num_sms;
+  kern<<<grid, kThreads, C::kTotal, stream>>>(maps[0], maps[1], p);
+  return cudaGetLastError();
+}
+
 template <int CG, int BN, bool A_MN, bool B_MN, int EPI>
 static cudaError_t launch(const CUtensorMap* maps, const TcParams& p, int num_sms, cudaStream_t stream) {
-  using C = Cfg<CG, BN>;
-  static_assert(!B_MN || (C::kBRows % 64 == 0), "an MN-major B tile is made of 64-column panels");
+  using C = Cfg<CG, BN, B_MN>;
   const int num_m = (p.M + CG * BLOCK_M - 1) / (CG * BLOCK_M), num_n = (p.N + BN - 1) / BN;
   int units = num_m * num_n;
   if (units > num_sms / CG) units = num_sms / CG;
@@ -416,6 +596,34 @@ static cudaError_t launch(const CUtensorMap* maps, const TcParams& p, int num_sm
 }  // namespace tc
 }  // namespace nrl
 
+extern "C" cudaError_t nrl_gemm_tc_batched(const CUtensorMap* maps, const nrl::tc::TcParams* p, int cg, int bn, int num_sms,
+                                           cudaStream_t stream) {
+  using namespace nrl::tc;
+  if (p->batch < 1 || p->K2 != 0) return cudaErrorInvalidValue;
+  if (cg == 1 && bn == 128) return launch_batched<1, 128>(maps, *p, num_sms, stream);
+  if (cg == 1 && bn == 256) return launch_batched<1, 256>(maps, *p, num_sms, stream);
+  if (cg == 2 && bn == 128) return launch_batched<2, 128>(maps, *p, num_sms, stream);
+  if (cg == 2 && bn == 256) return launch_batched<2, 256>(maps, *p, num_sms, stream);
+  return cudaErrorInvalidValue;
+}
+
+// split-K variant (cta_group::1, bf16 output with plain stores, no second operand pair); maps = {A, B}
+extern "C" cudaError_t nrl_gemm_tc_splitk(const CUtensorMap* maps, const nrl::tc::TcParams* p, int bn, int a_mn, int b_mn, int num_sms,
+                                          cudaStream_t stream) {
+  using namespace nrl::tc;
+  if (p->splits < 1 || p->ws == nullptr || p->counters == nullptr || p->out_bf16 == nullptr || p->K2 != 0) return cudaErrorInvalidValue;
+#define NRL_TC_SPLIT(BN_, AMN_, BMN_) \
+  if (bn == BN_ && a_mn == (AMN_ ? 1 : 0) && b_mn == (BMN_ ? 1 : 0)) return launch_splitk<BN_, AMN_, BMN_>(maps, *p, num_sms, stream);
+  NRL_TC_SPLIT(64, false, false)
+  NRL_TC_SPLIT(128, false, false)
+  NRL_TC_SPLIT(64, false, true)
+  NRL_TC_SPLIT(128, false, true)
+  NRL_TC_SPLIT(64, true, true)
+  NRL_TC_SPLIT(128, true, true)
+#undef NRL_TC_SPLIT
+  return cudaErrorInvalidValue;
+}
+
 // maps = {A, B, A2, B2, D}; operand boxes (tma_host.h): K-major operand [rows, K]: box {rows = 128 (A) | BN/CG (B), 64};
 // MN-major operand [K, cols]: box {64, 64}; D: box {128, 64}.  Unused maps may repeat a valid one.
 extern "C" cudaError_t nrl_gemm_tc(const CUtensorMap* maps, const nrl::tc::TcParams* p, int cg, int bn, int a_mn, int b_mn,
@@ -432,12 +640,17 @@ extern "C" cudaError_t nrl_gemm_tc(const CUtensorMap* maps, const nrl::tc::TcPar
   NRL_TC_CASE(2, 128, false, false, EPI_BF16)
   NRL_TC_CASE(2, 192, false, false, EPI_BF16)
   NRL_TC_CASE(2, 256, false, false, EPI_BF16)
+  NRL_TC_CASE(1, 128, false, false, EPI_SWIGLU)
+  NRL_TC_CASE(1, 256, false, false, EPI_SWIGLU)
+  NRL_TC_CASE(2, 128, false, false, EPI_SWIGLU)
+  NRL_TC_CASE(2, 256, false, false, EPI_SWIGLU)
   // K-major x MN-major ("NN": dgrad  dX = dY W, dH = dZ W_lm)
   NRL_TC_CASE(1, 64, false, true, EPI_BF16)
   NRL_TC_CASE(1, 128, false, true, EPI_BF16)
   NRL_TC_CASE(1, 192, false, true, EPI_BF16)
   NRL_TC_CASE(1, 256, false, true, EPI_BF16)
   NRL_TC_CASE(2, 128, false, true, EPI_BF16)
+  NRL_TC_CASE(2, 192, false, true, EPI_BF16)
   NRL_TC_CASE(2, 256, false, true, EPI_BF16)
   // MN-major x MN-major ("NT": wgrad  dW = dY^T X)
   NRL_TC_CASE(1, 64, true, true, EPI_BF16)

@@ -148,11 +148,10 @@ def _bias_tables(x: torch.Tensor, pos: torch.Tensor) -> torch.Tensor:
     T, H, dh = x.shape
     NB = pos.shape[1]
     if x.is_cuda and x.dtype == torch.bfloat16 and ops.use_native(x) and dh % 8 == 0 and NB % 8 == 0:
-        from ..ops import linear as _lin
-        out = torch.empty(H, T, NB, dtype=x.dtype, device=x.device)
-        for h in range(H):
-            _lin.gemm(x[:, h], pos[h], out=out[h])
-        return out
+        from ..ops import native
+        native._count()
+        # one batched launch: 3D TMA maps address the per-head [T, dh] / [NB, dh] slices in place
+        return native.ext().gemm_tc_batched(x.transpose(0, 1), pos, None)
     return torch.bmm(x.transpose(0, 1), pos.transpose(1, 2)).contiguous()
 
 

@@ -82,7 +82,7 @@ class LoraLinear(nn.Module):
 
     def forward(self, x):
         if isinstance(self.lora_dropout, nn.Identity) and not self.base_layer.weight.requires_grad:
-            # one dual-source-K tcgen05 GEMM per direction on CUDA (ops/linear.py); PyTorch oracle elsewhere
+            # one dual-source-K tcgen05 GEMM per direction on CUDA (ops/gemm.py); PyTorch oracle elsewhere
             return ops.lora_linear(x, self.base_layer.weight, self.base_layer.bias, self.lora_A.weight,
                                    self.lora_B.weight, self.scaling)
         y = self.base_layer(x)

@@ -96,7 +96,7 @@ class Qwen2Config:
 
 class Linear(nn.Linear):
     """``nn.Linear`` (same parameters, same checkpoint names) whose three contractions -- forward, dgrad, wgrad -- run on
-    the general tcgen05 GEMM (ops/linear.py) instead of cuBLAS."""
+    the general tcgen05 GEMM (ops/gemm.py) instead of cuBLAS."""
 
     def forward(self, x):
         return ops.linear(x, self.weight, self.bias)

@@ -81,10 +81,10 @@ def swiglu_pair(gate, up):
 
 
 def linear(x, weight, bias=None, act: int = 0):
-    """``F.linear`` (+ optional fused exact GELU, ``act=1``) -- the general tcgen05 GEMM on CUDA bf16 (ops/linear.py)."""
+    """``F.linear`` (+ optional fused exact GELU, ``act=1``) -- the general tcgen05 GEMM on CUDA bf16 (ops/gemm.py)."""
     if use_native(x):
         _nat()
-        from . import linear as _lin
+        from . import gemm as _lin
         return _lin.linear(x, weight, bias, act)
     y = torch.nn.functional.linear(x, weight, bias)
     return torch.nn.functional.gelu(y) if act == 1 else y
@@ -94,7 +94,7 @@ def lora_linear(x, weight, bias, lora_a, lora_b, scaling: float):
     """``x W^T + b + scaling * (x A^T) B^T`` with a frozen ``W``; one dual-source-K GEMM per direction on CUDA bf16."""
     if use_native(x):
         _nat()
-        from . import linear as _lin
+        from . import gemm as _lin
         if _lin.lora_supported(x, weight, lora_a, lora_b):
             return _lin.lora_linear(x, weight, bias, lora_a, lora_b, scaling)
     return ref.lora_linear(x, weight, bias, lora_a, lora_b, scaling)

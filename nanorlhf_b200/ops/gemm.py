@@ -44,10 +44,11 @@ def _rows(x: torch.Tensor) -> torch.Tensor:
 
 
 def gemm(a, b, a_mn=False, b_mn=False, a2=None, b2=None, bias=None, act=0, alpha=1.0, out=None, out_f32=None,
-         accumulate=False, cg=0, block_n=0):
+         accumulate=False, cg=0, block_n=0, split_k=-1):
     """Thin wrapper over ``_C.gemm_tc`` (see csrc/bindings.cpp) that counts the launch."""
     _native_mod._count()
-    return _native_mod.ext().gemm_tc(a, b, a_mn, b_mn, a2, b2, bias, act, alpha, out, out_f32, accumulate, cg, block_n)
+    return _native_mod.ext().gemm_tc(a, b, a_mn, b_mn, a2, b2, bias, act, alpha, out, out_f32, accumulate, cg, block_n,
+                                     split_k)
 
 
 class _LinearFn(torch.autograd.Function):

@@ -56,8 +56,8 @@ def gemm_bf16(a, b, bias=None, out=None, block_n: int = 0, act: int = 0):
 
 
 def linear(x, w, b=None, act: int = 0):
-    """y = x W^T + b with forward / dgrad / wgrad on the general tcgen05 GEMM (ops/linear.py)."""
-    from . import linear as _lin
+    """y = x W^T + b with forward / dgrad / wgrad on the general tcgen05 GEMM (ops/gemm.py)."""
+    from . import gemm as _lin
     return _lin.linear(x, w, b, act)
 
 
@@ -205,7 +205,7 @@ class _LmHeadLogprobFn(torch.autograd.Function):
         dh = torch.empty_like(h) if need_h else None
         dw = torch.zeros(weight.shape, dtype=torch.float32, device=weight.device) if need_w else None
         T = h.shape[0]
-        from . import linear as _lin
+        from . import gemm as _lin
         for s in range(0, T, _LmHeadLogprobFn.CHUNK):
             e = min(T, s + _LmHeadLogprobFn.CHUNK)
             _count()

@@ -20,7 +20,7 @@ from typing import Dict, List, Optional, Sequence
 import torch
 
 from ..models.lora import LoraLinear
-from ..ops import native, reference as ref
+from ..ops import gemm as _gemm, native, reference as ref
 from ..ops.attention import attention_varlen
 
 
@@ -95,7 +95,7 @@ class NativeSampler:
             xq, xs = native.ext().quant_rows_e4m3(x)
             wq, ws = lw.q8[name]
             return native.ext().gemm_fp8(xq, xs, wq, ws, bias, False)
-        return native.gemm_bf16(x, getattr(lw, name), bias)
+        return _gemm.gemm(x, getattr(lw, name), bias=bias, split_k=0)      # general tcgen05 GEMM (cta_group::2 where it pays)
 
     def quantize_arena(self):
         """fp8 rollout (rollout_dtype="fp8"): e4m3 copies of the merged arena with per-output-channel scales."""
@@ -195,9 +195,9 @@ class NativeSampler:
             return native.ext().swiglu(native.ext().gemm_fp8(hq, hs, wq, ws, None, False))
         if lw.wgu_i is not None:
             native._count()
-            return native.ext().gemm_swiglu(h, lw.wgu_i, None)
-        native._count(2)
-        return native.ext().swiglu(native.gemm_bf16(h, lw.wgu))
+            return native.ext().gemm_tc_swiglu(h, lw.wgu_i, None)
+        native._count(1)
+        return native.ext().swiglu(_gemm.gemm(h, lw.wgu, split_k=0))
 
     def _layer_decode(self, li, x, res, cos, sin, st):
         cfg, lw = self.cfg, self.layers[li]
@@ -229,7 +229,7 @@ class NativeSampler:
     def _final_logits(self, x, res):
         cfg = self.cfg
         h, _ = native.add_rmsnorm(x, res, self.lm.model.norm.weight, cfg.rms_norm_eps)
-        return native.gemm_bf16(h, self.lm.lm_head.weight)
+        return _gemm.gemm(h, self.lm.lm_head.weight, split_k=0)
 
     # ------------------------------------------------------------------------------------------
     # prefill

@@ -39,15 +39,15 @@ SHAPES = [(128, 256, 64), (300, 520, 200), (2048, 1536, 1536), (1000, 64, 512), 
 def test_tn(cg, bn, M, N, K):
     a, b, want = _operands(M, N, K, False, False)
     bias = torch.randn(N, device="cuda").bfloat16()
-    got = _ext().gemm_tc(a, b, False, False, None, None, bias, 0, 1.0, None, None, False, cg, bn)
+    got = _ext().gemm_tc(a, b, False, False, None, None, bias, 0, 1.0, None, None, False, cg, bn, 0)
     _check(got, want + bias.float(), k=K)
 
 
-@pytest.mark.parametrize("cg,bn", [(1, 64), (1, 128), (1, 192), (1, 256), (2, 128), (2, 256)])
+@pytest.mark.parametrize("cg,bn", [(1, 64), (1, 128), (1, 192), (1, 256), (2, 128), (2, 192), (2, 256)])
 @pytest.mark.parametrize("M,N,K", SHAPES)
 def test_b_mn_dgrad_form(cg, bn, M, N, K):
     a, b, want = _operands(M, N, K, False, True)
-    got = _ext().gemm_tc(a, b, False, True, None, None, None, 0, 0.5, None, None, False, cg, bn)
+    got = _ext().gemm_tc(a, b, False, True, None, None, None, 0, 0.5, None, None, False, cg, bn, 0)
     _check(got, 0.5 * want, k=K)
 
 
@@ -55,29 +55,29 @@ def test_b_mn_dgrad_form(cg, bn, M, N, K):
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (1536, 64, 6912), (64, 1536, 3000), (1024, 264, 520)])
 def test_both_mn_wgrad_form(cg, bn, M, N, K):
     a, b, want = _operands(M, N, K, True, True)
-    got = _ext().gemm_tc(a, b, True, True, None, None, None, 0, 1.0, None, None, False, cg, bn)
+    got = _ext().gemm_tc(a, b, True, True, None, None, None, 0, 1.0, None, None, False, cg, bn, 0)
     _check(got, want, k=K)
     acc = torch.randn(M, N, device="cuda")
     base = acc.clone()
     _ext().gemm_tc(a, b, True, True, None, None, None, 0, 2.0, None, acc, True, cg, bn)
     _check(acc, base + 2.0 * want, k=K)
-    _ext().gemm_tc(a, b, True, True, None, None, None, 0, 1.0, None, acc, False, cg, bn)
+    _ext().gemm_tc(a, b, True, True, None, None, None, 0, 1.0, None, acc, False, cg, bn, 0)
     _check(acc, want, k=K)
 
 
 @pytest.mark.parametrize("b_mn", [False, True])
-@pytest.mark.parametrize("cg,bn", [(1, 128), (1, 256), (2, 128), (2, 256)])
+@pytest.mark.parametrize("cg,bn", [(1, 128), (1, 256), (2, 128), (2, 192), (2, 256)])
 def test_dual_source_k_lora(cg, bn, b_mn):
     """y = x W^T + t B^T as ONE GEMM (t = s x A^T is the second A operand): the LoRA forward / dgrad form."""
     M, N, K, r = 1000, 1536, 1024, 64
     a, b, want = _operands(M, N, K, False, b_mn, seed=1)
     a2, b2, want2 = _operands(M, N, r, False, b_mn, seed=2)
-    got = _ext().gemm_tc(a, b, False, b_mn, a2, b2, None, 0, 1.0, None, None, False, cg, bn)
+    got = _ext().gemm_tc(a, b, False, b_mn, a2, b2, None, 0, 1.0, None, None, False, cg, bn, 0)
     _check(got, want + want2, k=K + r)
     # the second operand pair may be a column slice of a wider buffer (q / k / v adapters share one projection)
     wide = torch.randn(M, 3 * r, device="cuda").bfloat16()
     if not b_mn:
-        got = _ext().gemm_tc(a, b, False, False, wide[:, r:2 * r], b2, None, 0, 1.0, None, None, False, cg, bn)
+        got = _ext().gemm_tc(a, b, False, False, wide[:, r:2 * r], b2, None, 0, 1.0, None, None, False, cg, bn, 0)
         _check(got, want + wide[:, r:2 * r].float() @ b2.float().t(), k=K + r)
 
 
@@ -86,3 +86,46 @@ def test_auto_dispatch_and_gelu():
     bias = torch.randn(4096, device="cuda").bfloat16()
     got = _ext().gemm_tc(a, b, False, False, None, None, bias, 1)
     _check(got, torch.nn.functional.gelu(want + bias.float()), k=1024)
+
+
+@pytest.mark.parametrize("form,M,N,K", [("NT", 64, 1536, 6912), ("NT", 1536, 64, 6912), ("NT", 8960, 64, 3000), ("NT", 128, 1536, 6912),
+                                        ("TN", 6912, 64, 1536), ("NN", 6912, 64, 8960), ("NN", 1000, 64, 1536), ("TN", 300, 128, 4096)])
+@pytest.mark.parametrize("split_k", [-1, 1, 3, 16])
+def test_split_k(form, M, N, K, split_k):
+    """Small outputs with long contractions (LoRA wgrads, rank-r projections): split-K with the in-kernel ordered fix-up."""
+    a_mn, b_mn = form == "NT", form in ("NN", "NT")
+    a, b, want = _operands(M, N, K, a_mn, b_mn, seed=3)
+    ext = _ext()
+    for _ in range(2):                                # the tile counters must reset themselves between launches
+        got = ext.gemm_tc(a, b, a_mn, b_mn, None, None, None, 0, 0.25, None, None, False, 0, 0, split_k)
+        _check(got, 0.25 * want, k=K)
+    # split order is fixed -> bitwise reproducible
+    again = ext.gemm_tc(a, b, a_mn, b_mn, None, None, None, 0, 0.25, None, None, False, 0, 0, split_k)
+    assert torch.equal(got, again)
+
+
+@pytest.mark.parametrize("cg,bn", [(1, 128), (1, 256), (2, 128), (2, 256), (0, 0)])
+def test_swiglu_epilogue(cg, bn):
+    """gate_up projection with silu(gate) * up formed on the accumulator tile (interleaved weight rows)."""
+    torch.manual_seed(0)
+    for (M, F, K) in ((300, 512, 256), (1024, 8960, 1536), (77, 128, 128)):
+        x = torch.randn(M, K, device="cuda").bfloat16()
+        wg = (torch.randn(F, K, device="cuda") * 0.05).bfloat16()
+        wu = (torch.randn(F, K, device="cuda") * 0.05).bfloat16()
+        wi = torch.empty(2 * F, K, device="cuda", dtype=torch.bfloat16)
+        wi.view(F // 32, 2, 32, K).copy_(torch.stack([wg.view(F // 32, 32, K), wu.view(F // 32, 32, K)], 1))
+        out = _ext().gemm_tc_swiglu(x, wi, None, cg, bn)
+        g, u = x.float() @ wg.float().t(), x.float() @ wu.float().t()
+        _check(out, torch.nn.functional.silu(g) * u, rel=2e-2, k=K)
+
+
+@pytest.mark.parametrize("cg,bn", [(1, 128), (1, 256), (2, 128), (2, 256), (0, 0)])
+def test_batched_strided_heads(cg, bn):
+    """out[h] = x[:, h] pos[h]^T with x a packed [T, H, dh] projection (the DeBERTa bias tables): 3D TMA, no copies."""
+    torch.manual_seed(0)
+    for (T, H, dh, NB) in ((1000, 16, 64, 512), (300, 4, 64, 136), (26560 // 8, 16, 64, 512)):
+        x = torch.randn(T, H, dh, device="cuda").bfloat16()
+        pos = torch.randn(NB, H, dh, device="cuda").bfloat16().transpose(0, 1)          # [H, NB, dh] view
+        out = _ext().gemm_tc_batched(x.transpose(0, 1), pos, None, cg, bn)
+        want = torch.bmm(x.float().transpose(0, 1), pos.float().transpose(1, 2))
+        _check(out, want, k=dh)

@@ -448,12 +448,13 @@ def test_sampler_fp8_rollout_close_to_bf16():
     assert (oa[:, 0] == ob[:, 0]).float().mean().item() >= 0.75      # greedy first tokens mostly agree under fp8 noise
 
 
-@pytest.mark.parametrize("Hq,Hkv,splits", [(12, 2, 1), (28, 4, 2)])
-def test_paged_decode_fp8_kv(Hq, Hkv, splits):
+@pytest.mark.parametrize("Hq,Hkv,splits,max_ctx", [(12, 2, 1, 200), (28, 4, 2, 200), (12, 2, 1, 1700), (12, 2, 4, 3000)])
+def test_paged_decode_fp8_kv(Hq, Hkv, splits, max_ctx):
     n = _native()
     torch.manual_seed(0)
-    S, D, bs, nblk = 21, 128, 16, 400
-    ctx = torch.randint(1, 200, (S,), device="cuda", dtype=torch.int32)
+    S, D, bs = 21, 128, 16
+    nblk = S * ((max_ctx + bs - 1) // bs) + 8
+    ctx = torch.randint(1, max_ctx, (S,), device="cuda", dtype=torch.int32)
     ctx[0], ctx[1] = 1, 16
     maxb = int((ctx.max().item() + bs - 1) // bs)
     table = torch.randperm(nblk, device="cuda")[: S * maxb].view(S, maxb).to(torch.int32)
@@ -468,8 +469,10 @@ def test_paged_decode_fp8_kv(Hq, Hkv, splits):
     slots = torch.arange(T, device="cuda", dtype=torch.int32)
     n.ext().kv_cache_write_fp8(k, v, kq, vq, ks, vs, slots, None)
     kd = (kq.view(torch.float8_e4m3fn).float() * ks[..., None]).bfloat16()
-    vd = (vq.view(torch.float8_e4m3fn).float() * vs[..., None]).bfloat16()
+    # V pages are stored transposed ([128 d][16 tokens]) so the P.V operand fragments are single 32-bit loads
+    vd = (vq.view(nblk, Hkv, D, bs).transpose(2, 3).contiguous().view(torch.float8_e4m3fn).float() * vs[..., None]).bfloat16()
     assert _rel(kd.permute(0, 2, 1, 3).reshape(T, Hkv, D), k) < 0.05
+    assert _rel(vd.permute(0, 2, 1, 3).reshape(T, Hkv, D), v) < 0.05
     q = torch.randn(S, Hq, D, device="cuda").bfloat16()
     out = n.ext().paged_decode_fp8(q, kq, vq, ks, vs, table, ctx, 1.0 / math.sqrt(D), splits)
     want = ref.paged_attention_decode(q, kd, vd, table, ctx)      # oracle on the dequantised cache
