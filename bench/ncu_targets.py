@@ -64,4 +64,31 @@ if which in ("all", "attn_tc"):
     for _ in range(2):
         o, lse = native.ext().attn_fwd_tc(q, k, v, cu, 1 / math.sqrt(128))
     native.ext().attn_bwd_tc(torch.randn_like(o), q, k, v, o, lse, cu, 1 / math.sqrt(128))
+if which in ("all", "gemm_tc_ffn1", "gemm_tc_gate", "gemm_tc_dgrad", "gemm_tc_wgrad"):
+    shapes = {"gemm_tc_ffn1": (26560, 4096, 1024, False, False), "gemm_tc_gate": (6912, 8960, 1536, False, False),
+              "gemm_tc_dgrad": (6912, 1536, 8960, False, True), "gemm_tc_wgrad": (8960, 64, 6912, True, True)}
+    for name, (M, N, K, amn, bmn) in shapes.items():
+        if which not in ("all", name):
+            continue
+        a = torch.randn((K, M) if amn else (M, K), device=dev, dtype=torch.bfloat16)
+        b = torch.randn((K, N) if bmn else (N, K), device=dev, dtype=torch.bfloat16)
+        for _ in range(3):
+            native.ext().gemm_tc(a, b, amn, bmn)
+if which in ("all", "decode_fp8"):
+    S, ctx, Hq, Hkv, D = 1024, 1000, 12, 2, 128
+    per = ctx // 16 + 1
+    kq = torch.randint(0, 120, (S * per, Hkv, 16, D), device=dev, dtype=torch.uint8)
+    vq = torch.randint(0, 120, (S * per, Hkv, D, 16), device=dev, dtype=torch.uint8)
+    ks = torch.rand(S * per, Hkv, 16, device=dev) * 0.01 + 0.001
+    vs = torch.rand(S * per, Hkv, 16, device=dev) * 0.01 + 0.001
+    bt = torch.arange(S * per, device=dev, dtype=torch.int32).view(S, per)
+    cl = torch.full((S,), ctx, device=dev, dtype=torch.int32)
+    q = torch.randn(S, Hq, D, device=dev, dtype=torch.bfloat16)
+    for _ in range(3):
+        native.ext().paged_decode_fp8(q, kq, vq, ks, vs, bt, cl, 1 / math.sqrt(D), 1)
+if which in ("all", "sample"):
+    logits = torch.randn(1024, 151936, device=dev, dtype=torch.bfloat16)
+    rid = torch.arange(1024, device=dev, dtype=torch.int32)
+    for _ in range(3):
+        native.sample(logits, 0.9, 0.95, 1, 0, rid, rid)
 torch.cuda.synchronize()

@@ -30,9 +30,9 @@ base_model = "Qwen/Qwen2-1.5B"          # the reference script uses Qwen2-1.5B (
 @dataclass
 class GRPOConfig(RLConfig):
     grpo_sample_N: int = 4
-    memory_log: Optional[str] = None
+    memory_log: Optional[str] = None     # path of a JSONL file: per-update peak allocated / reserved HBM and phase times
     accuracy_before_train: bool = True
-    q_lora: bool = False
+    q_lora: bool = False                 # 4-bit base weights (bitsandbytes) in the reference; rejected here, see __main__
     accuracy_dataset_name: str = "HuggingFaceH4/MATH-500"
     eval_every: int = 10                 # hard-coded in the reference (grpo_r1_trainer.py:824)
     reward_match: str = "equiv"          # "exact" = the shipped reference's effective rule
@@ -86,7 +86,7 @@ class R1Trainer(SparseGRPOTrainer):
         if self.accuracy_func is not None and update % self.args.eval_every == 0:
             acc = float(self.accuracy_func(self.model, self.args))
             self.log({"eval_accuracy_new": acc,
-                      "eval_response_length": getattr(self.accuracy_func, "last_mean_response_chars", 0.0)})
+                      "eval_response_length": getattr(self.accuracy_func, "last_mean_response_tokens", 0.0)})
 
 
 GRPOTrainer = R1Trainer      # the name the reference exports
@@ -111,6 +111,10 @@ class _StringRewardAdapter:
 
 if __name__ == "__main__":
     training_args.apply_overrides()
+    if training_args.q_lora:
+        # reference: prepare_model_for_kbit_training on a bitsandbytes 4-bit base (grpo_r1.py:378-381).  A 1.5B / 7B bf16 base
+        # is 3 / 15 GB of a 180 GB B200, so the memory saving buys nothing here and no 4-bit GEMM path is built.
+        raise NotImplementedError("q_lora=True (4-bit base weights) is not supported: keep the frozen base in bf16 on B200")
     entry.prepare_output_dir(training_args)
     tokenizer, policy, ref_policy = entry.load_tokenizer_and_policies(training_args)
     train_rows, eval_rows = load_problems(training_args)

@@ -97,7 +97,7 @@ class RLConfig:
     adam_beta1: float = 0.9
     adam_beta2: float = 0.999
     adam_epsilon: float = 1e-8
-    max_grad_norm: Optional[float] = None       # the reference never clips (no clip call in the loop)
+    max_grad_norm: Optional[float] = None       # None = never clip (the reference); a value clips the global (all-rank) gradient norm
     warmup_steps: int = 0
     lr_scheduler_type: str = "cosine_with_min_lr"
     lr_scheduler_kwargs: Dict[str, Any] = field(default_factory=lambda: {"min_lr_rate": 0.1})
@@ -128,8 +128,10 @@ class RLConfig:
     offload_ref: Optional[str] = None
     offload_reward: Optional[str] = None
     offload_optimizer: Optional[str] = None
-    scratch_dir: str = "/tmp/nanorlhf_scratch"  # the reference hard-codes /data/temp_vllm_model
-    profile: str = "none"                       # none | nvtx | torch
+    scratch_dir: str = "/tmp/nanorlhf_scratch"  # profiler traces + value pre-fit scratch (reference: /data/temp_vllm_model, /data/cache_value_model)
+    profile: str = "none"                       # none | nvtx (ranges per phase) | torch (chrome trace of update `profile_update`)
+    profile_update: int = 2
+    memory_log: Optional[str] = None            # JSONL path: per-update peak HBM + phase times (r1's unused `memory_log`, grpo_r1.py:98-100)
     watchdog_timeout_s: float = 1800.0
 
     # ---- derived (filled by the trainer; reference: grpo_trainer.py:220-240) ------------------

@@ -95,6 +95,8 @@ class FusedAdamW(torch.optim.Optimizer):
             self.comm_mode = "nccl"          # csrc/comm.cu instantiates the P2P kernel for 2 / 4 / 8 ranks
         self.state_dtype = state_dtype
         self.master_weights = master_weights
+        self.max_grad_norm: Optional[float] = None      # set by the trainer (config.max_grad_norm)
+        self.last_grad_norm: Optional[float] = None
         self.comm_events: List[tuple] = []      # (start, end) CUDA events around every collective of step()
         self._flats: List[_Flat] = []
         self._fused = None
@@ -138,9 +140,22 @@ class FusedAdamW(torch.optim.Optimizer):
             return 0, f.padded
         return shard_bounds(f.padded, self.world, self.rank)
 
+    def _clip_factor(self) -> float:
+        """Global-norm clipping needs the norm of the REDUCED gradient before any parameter moves, so the gradients are
+        all-reduced first (NCCL) and this step then runs the local update on the already reduced buffers."""
+        if self.world > 1:
+            for f in self.flats:
+                self.comm.all_reduce_(f.grad, "sum")
+        norm = float(self.grad_norm()) * self.grad_scale / self.world
+        self.last_grad_norm = norm
+        return min(1.0, self.max_grad_norm / (norm + 1e-6))
+
     @torch.no_grad()
     def step(self, closure=None):
         self._step += 1
+        clip, reduced = 1.0, False
+        if self.max_grad_norm is not None and self.max_grad_norm > 0:
+            clip, reduced = self._clip_factor(), self.world > 1
         for g, f in zip(self.param_groups, self._flats):
             if f is None:
                 continue
@@ -152,18 +167,35 @@ class FusedAdamW(torch.optim.Optimizer):
             if timed:
                 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 ev0.record()
-            if self.comm_mode == "fused":
-                self._fused.allreduce_adam(f, hp, self.grad_scale / self.world)
+            if self.comm_mode == "fused" and not reduced:
+                self._fused.allreduce_adam(f, hp, clip * self.grad_scale / self.world)
+            elif self.comm_mode == "fused":
+                # clipped step: gradients already reduced; every rank updates its shard and the bf16 copies are re-gathered
+                lo_, hi_ = lo, hi
+                scale = clip * self.grad_scale / self.world
+                if ops.use_native(f.param):
+                    ops._nat().adamw_flat(f.param[lo_:hi_], f.grad[lo_:hi_], f.exp_avg, f.exp_avg_sq, scale=scale, master=f.master, **hp)
+                else:
+                    ref.adamw_step_(f.param[lo_:hi_], f.grad[lo_:hi_], f.exp_avg, f.exp_avg_sq, hp["lr"], b1, b2, hp["eps"], hp["wd"],
+                                    self._step, grad_scale=scale, master=f.master)
+                shards = self.comm.all_gather_cat(f.param[lo_:hi_].clone()) if (hi_ - lo_) * self.world == f.padded else None
+                if shards is not None:
+                    f.param.copy_(shards)
+                else:                                       # ragged last shard: broadcast each owner's slice
+                    for r in range(self.world):
+                        a_, b_ = shard_bounds(f.padded, self.world, r)
+                        self.comm.broadcast_(f.param[a_:b_], r)
             else:
                 if self.comm_mode == "nccl":
-                    self.comm.all_reduce_(f.grad, "sum")
-                    scale = self.grad_scale / self.world
+                    if not reduced:
+                        self.comm.all_reduce_(f.grad, "sum")
+                    scale = clip * self.grad_scale / self.world
                     if timed:                   # baseline: only the all-reduce is communication
                         ev1.record()
                         self.comm_events.append((ev0, ev1))
                         timed = False
                 else:
-                    scale = self.grad_scale
+                    scale = clip * self.grad_scale
                 if ops.use_native(f.param):
                     ops._nat().adamw_flat(f.param, f.grad, f.exp_avg, f.exp_avg_sq, scale=scale, master=f.master, **hp)
                 else:

@@ -56,6 +56,36 @@ def extract_answer_is(text: str) -> Optional[str]:
     return text[m[-1].end():].strip().rstrip(".").strip()
 
 
+_LAST_NUMBER_RE = re.compile(r"-?\d[\d,]*(?:\.\d+)?(?:/\d+)?|-?\.\d+")
+
+
+def extract_answer(text: str, dataset: str = "math") -> Optional[str]:
+    """Final answer of a free-form solution, in the order the reference's extractors try
+    (/root/reference/examples/r1-v0/utils/data_processing/answer_extraction.py:65-243, re-derived from their behaviour):
+    last ``\\boxed{}`` -> "final answer is $...$" (minerva) -> "the answer is ..." -> ``#### x`` (gsm8k) ->
+    a multiple-choice letter for ``dataset in {"mmlu", "sat", "aqua"}`` -> the last number in the text."""
+    if text is None:
+        return None
+    b = get_boxed(text)
+    if b is not None:
+        return b.strip()
+    m = re.search(r"[Ff]inal answer is:?\s*\$?(.+?)\$?(?:\.\s*I hope it is correct|\.?\s*$)", text.strip(), re.S)
+    if m:
+        return m.group(1).strip().strip("$").strip()
+    a = extract_answer_is(text)
+    if a is not None and a != "":
+        return a.split("\n")[0].strip().strip("$").rstrip(".").strip()
+    m = re.search(r"####\s*(.+)", text)
+    if m:
+        return m.group(1).strip().replace(",", "")
+    if dataset in ("mmlu", "sat", "aqua"):
+        m = re.findall(r"\(?\b([A-E])\b\)?", text)
+        if m:
+            return m[-1]
+    nums = _LAST_NUMBER_RE.findall(text)
+    return nums[-1].replace(",", "") if nums else None
+
+
 # --------------------------------------------------------------------------------------------------
 # normalisation (MATH "strip_string" family)
 # --------------------------------------------------------------------------------------------------
@@ -93,22 +123,27 @@ def _fix_sqrt(s: str) -> str:
     return re.sub(r"\\sqrt(\w)", r"\\sqrt{\1}", s)
 
 
-def strip_string(s: str) -> str:
+def strip_string(s: str, keep_equation: bool = False) -> str:
     s = str(s).strip()
     s = s.replace("\n", "").replace("\\!", "").replace("\\\\", "\\")
     s = s.replace("tfrac", "frac").replace("dfrac", "frac")
     s = s.replace("\\left", "").replace("\\right", "")
+    s = s.replace("\\{", "{").replace("\\}", "}")
     s = s.replace("^{\\circ}", "").replace("^\\circ", "").replace("°", "")
     s = s.replace("\\$", "").replace("$", "")
+    s = re.sub(r"(?<=[\d}])\s*\\(?:text|mbox|mathrm)\{[^}]*\}\s*$", "", s)        # trailing unit: 5\text{ cm}, 3\mathrm{m/s}
     s = re.sub(r"\\text\{\s*([^}]*)\}", r"\1", s)
     s = re.sub(r"\\mbox\{\s*([^}]*)\}", r"\1", s)
+    s = re.sub(r"\\mathrm\{\s*([^}]*)\}", r"\1", s)
+    s = re.sub(r"\\(?:mathbf|textbf|boldsymbol)\{([^}]*)\}", r"\1", s)
+    s = re.sub(r"(?:\\,|\\;|\\:|\\quad|\\qquad|~)", "", s)
     for u in _UNITS:
         s = re.sub(rf"(?<=[\d\s}}]){u}\b", "", s)
     s = s.replace("\\%", "").replace("%", "")
     s = s.replace(" .", " 0.").replace("{.", "{0.")
     if s.startswith("."):
         s = "0" + s
-    if len(s.split("=")) == 2 and len(s.split("=")[0]) <= 2:
+    if not keep_equation and len(s.split("=")) == 2 and len(s.split("=")[0]) <= 2:
         s = s.split("=")[1]
     s = _fix_sqrt(s)
     s = s.replace(" ", "")
@@ -124,8 +159,24 @@ def strip_string(s: str) -> str:
 # --------------------------------------------------------------------------------------------------
 # numeric / symbolic comparison
 # --------------------------------------------------------------------------------------------------
+_SCI_RE = re.compile(r"^(-?[\d.]+)(?:\\times|\\cdot|\*|x)10\^\{?(-?\d+)\}?$")
+
+
 def _to_float(s: str) -> Optional[float]:
-    s = s.replace(",", "")
+    if "," in s:
+        if not re.fullmatch(r"-?\d{1,3}(,\d{3})+(\.\d+)?", s):        # "1,3,5" is a list, "1,250.00" a number
+            return None
+        s = s.replace(",", "")
+    m = _SCI_RE.match(s)                              # 3.0\times10^{5}, 2\cdot10^-3 (OCW-style numeric answers)
+    if m:
+        try:
+            return float(m.group(1)) * 10.0 ** int(m.group(2))
+        except ValueError:
+            return None
+    m = re.fullmatch(r"(-?\d+)\\frac\{(\d+)\}\{(\d+)\}", s)           # mixed number 1\frac{1}{2}
+    if m and int(m.group(3)) != 0:
+        whole = int(m.group(1))
+        return whole + (-1 if whole < 0 else 1) * int(m.group(2)) / int(m.group(3))
     m = re.fullmatch(r"\\frac\{(-?[\d.]+)\}\{(-?[\d.]+)\}", s)
     try:
         if m:
@@ -197,12 +248,54 @@ def _split_elements(s: str) -> Optional[List[str]]:
     return None
 
 
+_MATRIX_RE = re.compile(r"\\begin\{(p|b|v|B|V)?matrix\}(.*?)\\end\{(?:p|b|v|B|V)?matrix\}|\\begin\{array\}(?:\{[^}]*\})?(.*?)\\end\{array\}", re.S)
+
+
+def _parse_matrix(s: str) -> Optional[List[List[str]]]:
+    r"""Rows x columns of a single LaTeX matrix / array environment (after ``strip_string`` the row separator is a single
+    backslash), None when ``s`` is not exactly one such environment."""
+    m = _MATRIX_RE.fullmatch(s)
+    if not m:
+        return None
+    body = m.group(2) if m.group(2) is not None else m.group(3)
+    rows = [r for r in re.split(r"\\\\|\\(?![a-zA-Z])", body) if r.strip() != ""]
+    return [[c.strip() for c in r.split("&")] for r in rows]
+
+
+def _top_level_split(s: str, sep: str = ",") -> List[str]:
+    depth, cur, parts = 0, "", []
+    for ch in s:
+        if ch in "([{":
+            depth += 1
+        elif ch in ")]}":
+            depth -= 1
+        if ch == sep and depth == 0:
+            parts.append(cur)
+            cur = ""
+        else:
+            cur += ch
+    parts.append(cur)
+    return parts
+
+
 def is_equiv(pred: str, gt: str, use_sympy: bool = True, timeout_s: float = 3.0) -> bool:
     if pred is None or gt is None:
         return False
     a, b = strip_string(pred), strip_string(gt)
     if a == b:
         return True
+    # matrices / vectors: same shape, element-wise equivalent; a column vector may also be written as a tuple
+    ma, mb = _parse_matrix(a), _parse_matrix(b)
+    if ma is not None or mb is not None:
+        if ma is None or mb is None:
+            other, mat = (a, mb) if ma is None else (b, ma)
+            flat = _split_elements(other)
+            if flat is None or not (all(len(r) == 1 for r in mat) or len(mat) == 1):
+                return False
+            cells = [r[0] for r in mat] if len(mat) > 1 else mat[0]
+            return len(cells) == len(flat) and all(is_equiv(x, y, use_sympy, timeout_s) for x, y in zip(cells, flat))
+        return (len(ma) == len(mb) and all(len(x) == len(y) for x, y in zip(ma, mb))
+                and all(is_equiv(x, y, use_sympy, timeout_s) for ra, rb in zip(ma, mb) for x, y in zip(ra, rb)))
     if a.lower() == b.lower() and not any(c.isdigit() for c in a):
         return True
     fa, fb = _to_float(a), _to_float(b)
@@ -213,11 +306,47 @@ def is_equiv(pred: str, gt: str, use_sympy: bool = True, timeout_s: float = 3.0)
         return len(pa) == len(pb) and all(is_equiv(x, y, use_sympy, timeout_s) for x, y in zip(pa, pb))
     ea, eb = _split_elements(a), _split_elements(b)
     if ea is not None and eb is not None:
+        # tuples / intervals: ordered, and the bracket types are part of the answer ((1,2] != [1,2]); {..} is a set
+        if a[0] == "{" and b[0] == "{":
+            return _multiset_equiv(ea, eb, use_sympy, timeout_s)
         return (len(ea) == len(eb) and a[0] == b[0] and a[-1] == b[-1]
                 and all(is_equiv(x, y, use_sympy, timeout_s) for x, y in zip(ea, eb)))
+    # bare comma lists ("1, 3, 5" / "x=1,2"): order-insensitive
+    if "," in a and "," in b and ea is None and eb is None:
+        la_, lb_ = _top_level_split(a), _top_level_split(b)
+        if len(la_) > 1 and len(lb_) > 1:
+            return _multiset_equiv(la_, lb_, use_sympy, timeout_s)
+    # equations: same solution set <=> lhs - rhs proportional; compare the differences up to sign
+    qa, qb = strip_string(pred, keep_equation=True), strip_string(gt, keep_equation=True)
+    if qa.count("=") == 1 and qb.count("=") == 1 and (len(qa.split("=")[0]) > 2 or len(qb.split("=")[0]) > 2):
+        (la, ra), (lb, rb) = qa.split("="), qb.split("=")
+        if use_sympy and symbolic_equal(f"({la})-({ra})", f"({lb})-({rb})", timeout_s):
+            return True
+        return bool(use_sympy and symbolic_equal(f"({la})-({ra})", f"-(({lb})-({rb}))", timeout_s))
+    # a numeric ground truth against an answer with words around exactly one number ("5 apples", "x = 5 units")
+    if fb is not None and fa is None:
+        nums = _LAST_NUMBER_RE.findall(a)
+        if len(nums) == 1:
+            f1 = _to_float(_fix_a_slash_b(nums[0].replace(",", "")))
+            if f1 is not None:
+                return numeric_equal(f1, fb)
     if use_sympy and len(a) < 200 and len(b) < 200:
         return symbolic_equal(a, b, timeout_s)
     return False
+
+
+def _multiset_equiv(xs: List[str], ys: List[str], use_sympy: bool, timeout_s: float) -> bool:
+    if len(xs) != len(ys):
+        return False
+    left = list(ys)
+    for x in xs:
+        for i, y in enumerate(left):
+            if is_equiv(x, y, use_sympy, timeout_s):
+                left.pop(i)
+                break
+        else:
+            return False
+    return True
 
 
 def iscorrect(answer: Optional[str], ground_truth: Optional[str], match: str = "equiv", timeout_s: float = 3.0) -> bool:
@@ -274,12 +403,17 @@ def make_accuracy_func(problems: Sequence[Dict[str, str]], tokenizer, template: 
         out = generate(1, model, tokenizer, prompts, 0.0, min(max_tokens, args.response_length), top_p=1.0, seed=42,
                        backend=args.sampler, rollout_dtype=args.rollout_dtype)
         texts = tokenizer.batch_decode(out)
-        good, lens = 0, []
+        # response length in TOKENS up to and including EOS (the reference logs token counts, grpo_r1.py:320-337)
+        stop = (out == tokenizer.pad_token_id)
+        if tokenizer.eos_token_id is not None:
+            after_eos = ((out == tokenizer.eos_token_id).long().cumsum(1) - (out == tokenizer.eos_token_id).long()) > 0
+            stop = stop | after_eos
+        tok_lens = (~stop).sum(1).float()
+        good = 0
         for p, t in zip(problems, texts):
             t = t.split(tokenizer.eos_token)[0].replace(tokenizer.pad_token, "")
-            lens.append(len(t))
             good += int(iscorrect(get_boxed(t), p["answer"], match))
-        accuracy_func.last_mean_response_chars = sum(lens) / max(len(lens), 1)
+        accuracy_func.last_mean_response_tokens = float(tok_lens.mean()) if len(problems) else 0.0
         return good / max(len(problems), 1)
 
     return accuracy_func

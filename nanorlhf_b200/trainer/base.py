@@ -118,6 +118,8 @@ class RLTrainer:
         if self.lr_scheduler is None:
             self.lr_scheduler = get_scheduler(args.lr_scheduler_type, self.optimizer, args.warmup_steps,
                                               args.num_total_batches, args.lr_scheduler_kwargs)
+        if hasattr(self.optimizer, "max_grad_norm"):
+            self.optimizer.max_grad_norm = args.max_grad_norm
         self.tiering.register_optimizer("optimizer", self.optimizer, args.role_residency("optimizer"))
 
         self.state = OnlineTrainerState(is_local_process_zero=self.comm.local_rank == 0,
@@ -282,7 +284,11 @@ class RLTrainer:
         metrics = {}
         start_update = self.state.global_step + 1
         for update in range(start_update, a.num_total_batches + 1):
-            metrics = self.train_one_update(update, next(it))
+            if a.profile == "torch" and update == start_update + max(a.profile_update - 1, 0) and self.comm.is_main:
+                metrics = self._profiled_update(update, next(it))
+            else:
+                metrics = self.train_one_update(update, next(it))
+            self._write_memory_log(update, metrics)
             self.lr_scheduler.step()
             self.control = self.callback_handler.on_step_end(a, self.state, self.control)
             # state.max_steps = batches * minibatches is never reached by global_step (SURVEY.md 3.5 "Schedules"),
@@ -299,8 +305,47 @@ class RLTrainer:
         if self.control.should_save:
             self._save_checkpoint(self.model, trial=None, metrics=metrics)
             self.control = self.callback_handler.on_save(a, self.state, self.control)
+        self._maybe_load_best()
         self.heartbeat.close()
         return metrics
+
+    def _profiled_update(self, update, data):
+        """``profile="torch"``: one update under torch.profiler (CPU + CUDA activities); chrome trace and a kernel table under
+        ``<scratch_dir>/profile``.  Numbers of this update are not benchmark numbers (profiler overhead)."""
+        from torch.profiler import ProfilerActivity, profile
+        acts = [ProfilerActivity.CPU] + ([ProfilerActivity.CUDA] if self.device.type == "cuda" else [])
+        out_dir = os.path.join(self.args.scratch_dir, "profile")
+        os.makedirs(out_dir, exist_ok=True)
+        with profile(activities=acts) as prof:
+            metrics = self.train_one_update(update, data)
+        prof.export_chrome_trace(os.path.join(out_dir, f"update{update}_rank{self.comm.rank}.json"))
+        with open(os.path.join(out_dir, f"update{update}_rank{self.comm.rank}.txt"), "w") as f:
+            f.write(prof.key_averages().table(sort_by="cuda_time_total" if self.device.type == "cuda" else "cpu_time_total", row_limit=60))
+        return metrics
+
+    def _write_memory_log(self, update, metrics):
+        path = getattr(self.args, "memory_log", None)
+        if not path or not self.comm.is_main:
+            return
+        import json
+        row = {"update": update, **{k: v for k, v in metrics.items() if k.startswith(("mem/", "time/"))}}
+        os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+        with open(path, "a") as f:
+            f.write(json.dumps(row) + "\n")
+
+    def _maybe_load_best(self):
+        """``load_best_model_at_end``: finish with the weights of ``state.best_model_checkpoint`` (HF semantics; the reference
+        sets the flag only to satisfy EarlyStoppingCallback and its overridden ``train`` never acts on it -- SURVEY.md 2.2)."""
+        a, best = self.args, self.state.best_model_checkpoint
+        if not a.load_best_model_at_end or a.save_strategy == "no" or not best or not os.path.isdir(best):
+            return
+        last = os.path.join(a.output_dir, f"{ckpt.PREFIX}-{self.state.global_step}")
+        if os.path.abspath(best) == os.path.abspath(last):
+            return
+        ckpt._load_model_into(self.policy, best)
+        self._bump_policy_version()
+        if self.comm.is_main:
+            print(f"[train] loaded the best checkpoint ({best}, {a.metric_for_best_model} = {self.state.best_metric})")
 
     def before_training(self):
         pass

@@ -94,7 +94,8 @@ class PromptLoader:
     """Shuffled, drop-last, rank-sharded, resumable batch iterator.
 
     All ranks draw the same permutation (seeded) and take interleaved shards -- the behaviour of an
-    accelerate-prepared DataLoader.  ``state_dict`` makes the dataloader
+    accelerate-prepared DataLoader.  ``drop_last=False`` keeps the tail of every epoch: the last
+    global batch is completed with the first prompts of the same permutation (the update needs full batches).  ``state_dict`` makes the dataloader
     position part of checkpoints (the reference cannot resume).
     """
 
@@ -109,7 +110,8 @@ class PromptLoader:
                              f"({batch_size} x {world_size})")
 
     def __len__(self):
-        return len(self.dataset) // (self.batch_size * self.world_size)
+        per_step = self.batch_size * self.world_size
+        return len(self.dataset) // per_step if self.drop_last else -(-len(self.dataset) // per_step)
 
     def _order(self) -> List[int]:
         idx = list(range(len(self.dataset)))
@@ -123,6 +125,9 @@ class PromptLoader:
             order = self._order()
             per_step = self.batch_size * self.world_size
             n_steps = len(order) // per_step
+            if not self.drop_last and len(order) % per_step:
+                n_steps += 1
+                order = order + order[:per_step - len(order) % per_step]
             while self.cursor < n_steps:
                 s = self.cursor * per_step
                 chunk = order[s:s + per_step][self.rank::self.world_size]

@@ -58,3 +58,31 @@ def test_cosine_with_min_lr():
         s.step()
     assert lrs[0] == 1.0 and all(a >= b for a, b in zip(lrs, lrs[1:]))
     assert abs(opt.param_groups[0]["lr"] - 0.1) < 1e-6
+
+
+def test_prompt_loader_drop_last_false_keeps_the_tail():
+    from nanorlhf_b200.utils.data import PromptLoader
+    ds = [{"i": i} for i in range(10)]
+    collate = lambda rows: [r["i"] for r in rows]            # noqa: E731
+    keep = PromptLoader(ds, 4, collate, seed=0, shuffle=False, drop_last=False)
+    drop = PromptLoader(ds, 4, collate, seed=0, shuffle=False, drop_last=True)
+    assert len(keep) == 3 and len(drop) == 2
+    it = iter(keep)
+    seen = [next(it) for _ in range(3)]
+    assert seen == [[0, 1, 2, 3], [4, 5, 6, 7], [8, 9, 0, 1]]
+    it = iter(drop)
+    assert [next(it) for _ in range(3)] == [[0, 1, 2, 3], [4, 5, 6, 7], [0, 1, 2, 3]]
+
+
+def test_max_grad_norm_clips_the_update():
+    import torch
+    from nanorlhf_b200.parallel.optimizer import FusedAdamW
+    w = torch.nn.Parameter(torch.zeros(1024))
+    opt = FusedAdamW([{"params": [w]}], lr=1e-2)
+    opt.max_grad_norm = 1.0
+    opt.zero_grad()
+    w.grad.fill_(10.0)                       # norm 320 -> scaled by 1/320
+    opt.step()
+    assert abs(opt.last_grad_norm - 320.0) < 1e-3
+    # Adam's first step is lr * sign(g) whatever the scale; the moments carry the clipped gradient
+    assert torch.allclose(opt.flats[0].exp_avg[:1024], torch.full((1024,), 0.1 * 10.0 / 320.0), rtol=1e-4)

@@ -38,3 +38,37 @@ def test_rule_reward_callback():
     r = rm.RuleMathReward({q: "5"}, match="equiv")
     s = r([prompt + r"2+3=5 so \boxed{5}<|im_end|>", prompt + r"\boxed{6}", prompt + "five"], None, "<|im_end|>")
     assert s.tolist() == [1.0, 0.0, 0.0]
+
+
+def test_grader_breadth_matrices_intervals_lists_units():
+    """Forms the reference's vendored graders cover (utils/eval/eval_utils.py:181-325, latex_answer_check.py:166-236)."""
+    try:
+        # matrices: element-wise, shape-sensitive; a column vector may be written as a tuple
+        assert rm.iscorrect(r"\begin{pmatrix} 1 & 2 \\ 3 & 4 \end{pmatrix}", r"\begin{pmatrix}1&2\\3&4.0\end{pmatrix}")
+        assert not rm.iscorrect(r"\begin{pmatrix} 1 & 2 \\ 3 & 5 \end{pmatrix}", r"\begin{pmatrix}1&2\\3&4\end{pmatrix}")
+        assert rm.iscorrect(r"\begin{pmatrix} \frac{1}{2} \\ 3 \end{pmatrix}", r"(0.5, 3)")
+        # intervals: bracket types are part of the answer; unions split on \cup; infinity
+        assert rm.iscorrect(r"(-\infty, 2]", r"(-\infty,2]") and not rm.iscorrect(r"(-\infty, 2)", r"(-\infty,2]")
+        assert rm.iscorrect(r"[1,2)\cup(3,4]", r"[1, 2) \cup (3, 4]")
+        # units in \text / \mathrm, degrees, dollars, percent
+        assert rm.iscorrect(r"5\text{ cm}", "5") and rm.iscorrect(r"3\mathrm{m}", "3") and rm.iscorrect(r"90^\circ", "90")
+        assert rm.iscorrect(r"\$1,250.00", "1250") and rm.iscorrect(r"50\%", "0.5") and rm.iscorrect("50", r"50\%")
+        # unordered lists and sets, ordered tuples
+        assert rm.iscorrect("1, 3, 5", "5,3,1") and rm.iscorrect(r"\{1,2\}", r"\{2,1\}") and not rm.iscorrect("(1,2)", "(2,1)")
+        # scientific notation, mixed numbers, a number embedded in words
+        assert rm.iscorrect(r"3.0\times 10^{5}", "300000") and rm.iscorrect(r"1\frac{1}{2}", "1.5")
+        assert rm.iscorrect("5 apples", "5") and not rm.iscorrect("5 apples and 6 pears", "5")
+        # equations: same solution set up to sign / rearrangement
+        assert rm.iscorrect("y=2x+1", "y = 1 + 2x") and rm.iscorrect("2x-y+1=0", "y=2x+1") and not rm.iscorrect("y=2x+1", "y=2x+2")
+    finally:
+        rm.shutdown_pool()
+
+
+def test_extract_answer_styles():
+    assert rm.extract_answer(r"thus \boxed{7} so final") == "7"
+    assert rm.extract_answer("Final Answer: The final answer is $x^2+1$. I hope it is correct.") == "x^2+1"
+    assert rm.extract_answer("so the answer is 12.") == "12"
+    assert rm.extract_answer("work work\n#### 1,234") == "1234"
+    assert rm.extract_answer("The correct option is (C)", dataset="mmlu") == "C"
+    assert rm.extract_answer("we get 3 then 4 and finally 19") == "19"
+    assert rm.extract_answer("nothing here") is None
