@@ -48,12 +48,25 @@ def timed(fn, iters=5):
     return float(t)
 
 
-res = {"world": comm.world_size, "identical_to_local_merge": bool(ok), "local_merge_ms": timed(lambda: refresh_sampler_arena(local)),
-       "sharded_peer_store_ms": timed(sync.refresh), "arena_gb": sync.flat.numel() * 2 / 1e9}
+t_local, t_sharded = timed(lambda: refresh_sampler_arena(local)), timed(sync.refresh)
+arena_gb = sync.flat.numel() * 2 / 1e9
+# K-BC roofline: every rank must RECEIVE (world-1)/world of the merged arena over NVLink (770 GB/s/dir measured) and read
+# 1/world of the base weights from HBM; the slower of the two bounds the refresh
+W = comm.world_size
+floor_ms = max(arena_gb * (W - 1) / W / 770.0, arena_gb / W / 6583.0) * 1e3
+verdict = torch.tensor([1 if ok else 0], device=dev)
+comm.all_reduce_(verdict, "min")
+ok = bool(verdict.item())
+res = {"world": W, "identical_to_local_merge": ok, "multicast": sync.stats["multicast"], "local_merge_ms": t_local,
+       "sharded_multicast_ms": t_sharded, "arena_gb": arena_gb, "nvlink_floor_ms": floor_ms,
+       "frac_of_nvlink_roofline": floor_ms / t_sharded}
 if comm.is_main:
     print(json.dumps(res), flush=True)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(res, open(os.path.join(ROOT, "gpurun_out", f"wsync_check_{comm.world_size}.json"), "w"))
+del sync, shared, local
+torch.cuda.synchronize()
 comm.barrier()
 comm.close()
-sys.exit(0 if ok else 1)
+sys.stdout.flush()
+os._exit(0 if ok else 1)

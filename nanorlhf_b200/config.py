@@ -123,6 +123,7 @@ class RLConfig:
 
     # ---- runtime (B200) --------------------------------------------------------------------
     comm: str = "fused"                         # fused (symmetric-memory kernels) | nccl
+    weight_sync: str = "sharded"                # sharded (K-BC: layer-sharded merge + multimem.st into every rank's arena) | local
     train_cuda_graph: str = "auto"              # auto | on | off : replay the micro-step (fwd+loss+bwd) as a CUDA graph
     offload_policy: str = "resident"            # per-role residency: resident | host
     offload_ref: Optional[str] = None

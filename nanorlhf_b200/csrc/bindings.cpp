@@ -431,7 +431,10 @@ torch::Tensor lmhead_dlogits(const torch::Tensor& hidden, const torch::Tensor& w
 }
 
 // K-BC: out[N_out, K_in] = W + scale * lora_B[N_out, r] @ lora_A[r, K_in], on the tcgen05 GEMM (contraction = r)
-void lora_merge(const torch::Tensor& w, const torch::Tensor& lora_a, const torch::Tensor& lora_b, double scale, torch::Tensor out) {
+// mc_out_ptr != 0: `out` is this rank's view of a symmetric (NVLS-multicast-bound) arena and mc_out_ptr the multicast address of
+// its first element -- the epilogue then stores with multimem.st into every rank's arena at once.
+void lora_merge(const torch::Tensor& w, const torch::Tensor& lora_a, const torch::Tensor& lora_b, double scale, torch::Tensor out,
+                int64_t mc_out_ptr) {
   check_bf16_2d(w, "w");
   check_bf16_2d(lora_b, "lora_B");
   check_bf16_2d(out, "out");
@@ -449,6 +452,11 @@ void lora_merge(const torch::Tensor& w, const torch::Tensor& lora_a, const torch
   p.M = N_out; p.N = K_in; p.K = r; p.n_splits = 1; p.scale = static_cast<float>(scale);
   p.addend = reinterpret_cast<const __nv_bfloat16*>(w.data_ptr());
   p.addend_stride = w.stride(0);
+  if (mc_out_ptr != 0) {
+    TORCH_CHECK(K_in % 8 == 0 && (mc_out_ptr & 15) == 0, "multicast merge needs 16-byte aligned rows");
+    p.mc_out = reinterpret_cast<__nv_bfloat16*>(mc_out_ptr);
+    p.mc_stride = out.stride(0);
+  }
   check(nrl_gemm_bf16_tn(&tmA, &tmB, &tmD, &p, bn, nrl::EPI_MERGE, num_sms(), cur_stream()), "lora_merge");
 }
 
@@ -934,7 +942,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("lmhead_logprob_fwd", &lmhead_logprob_fwd, py::arg("hidden"), py::arg("weight"), py::arg("targets"),
         py::arg("inv_temperature"), py::arg("n_splits") = 0);
   m.def("lmhead_dlogits", &lmhead_dlogits);
-  m.def("lora_merge", &lora_merge);
+  m.def("lora_merge", &lora_merge, py::arg("w"), py::arg("lora_a"), py::arg("lora_b"), py::arg("scale"), py::arg("out"),
+        py::arg("mc_out_ptr") = 0);
   m.def("quant_rows_e4m3", &quant_rows_e4m3);
   m.def("gemm_fp8", &gemm_fp8, py::arg("aq"), py::arg("a_scale"), py::arg("bq"), py::arg("b_scale"), py::arg("bias") = py::none(),
         py::arg("swiglu") = false);

@@ -325,6 +325,32 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               }
               store_buf ^= 1;
             }
+          } else if (EPI == EPI_MERGE && p.mc_out != nullptr) {
+            // ---- K-BC: W' = W + s B A straight into EVERY rank's sampler arena: one multimem.st per 16 bytes, the
+            //      NVSwitch replicates it (no per-peer recompute, no NCCL broadcast) ----
+            if (row_ok) {
+              __nv_bfloat16* mrow = p.mc_out + static_cast<long>(row) * p.mc_stride + col0;
+              const __nv_bfloat16* wrow = p.addend + static_cast<long>(row) * p.addend_stride + col0;
+#pragma unroll
+              for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                  const int col = col0 + h * 32 + j;
+                  if (col < p.N) {                      // N % 8 == 0 (checked on the host)
+                    const uint4 w8 = *reinterpret_cast<const uint4*>(wrow + h * 32 + j);
+                    const uint32_t ww[4] = {w8.x, w8.y, w8.z, w8.w};
+                    uint32_t o[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                      const float2 w2 = unpack_bf16x2(ww[q]);
+                      o[q] = pack_bf16x2(__uint_as_float(v[h][j + 2 * q]) * p.scale + w2.x,
+                                         __uint_as_float(v[h][j + 2 * q + 1]) * p.scale + w2.y);
+                    }
+                    asm volatile("multimem.st.relaxed.sys.global.v4.bf16x2 [%0], {%1,%2,%3,%4};"
+                                 ::"l"(mrow + h * 32 + j), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+                  }
+                }
+            }
           } else {
             // ---- bf16 tile store through swizzled smem + TMA ----
             uint8_t* buf = staging + store_buf * kStagingBytes;

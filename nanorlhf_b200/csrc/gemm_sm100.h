@@ -28,6 +28,10 @@ struct GemmParams {
   const __nv_bfloat16* addend;  // EPI_MERGE: [M, N] row-major, row stride addend_stride elements
   long addend_stride;
   int act;                      // EPI_STORE: 0 = none, 1 = exact (erf) GELU applied after the bias
+  // EPI_MERGE, K-BC across ranks: when non-null the merged tile is written with `multimem.st` to this NVLS multicast
+  // address (element [0,0] of D in every rank's sampler arena, row stride mc_stride elements) instead of a local TMA store
+  __nv_bfloat16* mc_out;
+  long mc_stride;
 };
 
 }  // namespace nrl

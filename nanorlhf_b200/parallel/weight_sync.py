@@ -8,13 +8,18 @@ an engine boot per update.
 Here the sampler keeps a fused arena (qkv / gate_up concatenated) and ``refresh_sampler_arena``
 rewrites it from the live training parameters:
 
-* LoRA layers:    W' = W + (alpha/r) * B @ A  -- fused kernel ``lora_merge`` (csrc/quant.cu): the rank-r
-                  product, the add, the optional fp8 (e4m3, 1x128 block scales) quantisation and the
-                  store into the arena happen in one pass over W;
+* LoRA layers:    W' = W + (alpha/r) * B @ A  -- the ``EPI_MERGE`` epilogue of the tcgen05 GEMM
+                  (csrc/gemm_sm100.cu): the rank-r product runs on the tensor cores (contraction = r), W is streamed
+                  into the epilogue, the merged tile goes straight into the arena -- one pass over W;
 * plain layers:   device copy into the fused layout;
-* data parallel:  the work is sharded by layer across ranks and each rank writes its merged tiles
-                  straight into every peer's arena over NVLink (symmetric memory) -- see
-                  ``refresh_sampler_arena_sharded``; with one GPU it degenerates to the local merge.
+* data parallel:  ``ShardedWeightSync`` -- the arena lives in symmetric memory bound to an NVLS multicast object; rank r
+                  merges only the layers with ``layer % world == r`` and its epilogue writes every merged tile with
+                  ``multimem.st`` to the multicast address, i.e. into ALL ranks' arenas at once (the NVSwitch replicates
+                  the store).  Per rank: 1/world of the merge math and of the HBM reads, no NCCL broadcast, no per-peer
+                  recompute.  Without a multicast object (or on one GPU) it degenerates to the local merge.
+* fp8 rollout:    ``rollout_dtype="fp8"`` re-quantises the refreshed arena (e4m3, one scale per output channel,
+                  csrc/quant.cu) in a second pass -- the per-channel amax needs the whole merged row, which spans
+                  several epilogue tiles.
 """
 from __future__ import annotations
 
@@ -85,15 +90,8 @@ def refresh_sampler_arena(sampler):
 # data-parallel variant: layer-sharded merge + peer stores over NVLink
 # ------------------------------------------------------------------------------------------------
 class ShardedWeightSync:
-    """K-BC across ranks: rank r merges (W + (alpha/r) B A) only for layers with ``layer % world == r`` and the
-    GEMM epilogue's TMA stores land directly in *every* rank's sampler arena (the arenas live in symmetric
-    memory, so a peer's arena is an ordinary global address over NVLink).  Per rank: 1/world of the merge
-    math and HBM reads, (world-1)/world of the arena arrives over NVLink instead of being recomputed.
-
-    Measured trade-off: when every rank already holds the full training weights a
-    *local* merge moves fewer bytes than receiving merged weights over NVLink, so ``refresh_sampler_arena``
-    stays the default; this path is for configurations where the merge inputs are sharded.
-    """
+    """K-BC across ranks (see the module docstring).  ``refresh`` = barrier, sharded merge with multicast stores,
+    barrier; plain (non-LoRA) layers, biases and norms are replicated locally."""
 
     def __init__(self, sampler, comm):
         import torch.distributed as dist
@@ -108,6 +106,7 @@ class ShardedWeightSync:
         self.per_layer = per_layer
         self.flat = symm_mem.empty(per_layer * cfg.num_hidden_layers, dtype=torch.bfloat16, device=sampler.device)
         self.hdl = symm_mem.rendezvous(self.flat, self.group.group_name)
+        self.mc_base = int(getattr(self.hdl, "multicast_ptr", 0) or 0)
         # re-point the sampler's arena at the symmetric buffer
         for li, lw in enumerate(sampler.layers):
             off = li * per_layer
@@ -115,6 +114,10 @@ class ShardedWeightSync:
                 getattr(lw, name)  # must exist
                 setattr(lw, name, self.flat[off:off + a * b].view(a, b))
                 off += a * b
+        self.stats = {"refreshes": 0, "multicast": bool(self.mc_base)}
+
+    def _mc_addr(self, view: torch.Tensor) -> int:
+        return self.mc_base + (view.data_ptr() - self.flat.data_ptr()) if self.mc_base else 0
 
     def _peer_view(self, peer: int, li: int, name: str):
         off = li * self.per_layer
@@ -123,6 +126,18 @@ class ShardedWeightSync:
                 return self.hdl.get_buffer(peer, (a, b), torch.bfloat16, off)
             off += a * b
         raise KeyError(name)
+
+    def _write(self, mod, li: int, name: str, rows: slice):
+        """Merged weight of ``mod`` into rows ``rows`` of arena matrix ``name`` of layer ``li`` on EVERY rank."""
+        local = getattr(self.sampler.layers[li], name)[rows]
+        if isinstance(mod, LoraLinear) and self.mc_base:
+            native._count()
+            native.ext().lora_merge(mod.base_layer.weight, mod.lora_A.weight, mod.lora_B.weight, float(mod.scaling), local,
+                                    self._mc_addr(local))
+            return
+        # no multicast object (or a plain layer that only this rank was asked to write): peer stores over NVLink
+        for peer in range(self.comm.world_size):
+            _merged(mod, self._peer_view(peer, li, name)[rows])
 
     @torch.no_grad()
     def refresh(self):
@@ -134,23 +149,22 @@ class ShardedWeightSync:
         for li in range(cfg.num_hidden_layers):
             layer, lw = s.lm.model.layers[li], s.layers[li]
             at, mlp = layer.self_attn, layer.mlp
-            if li % W == R:
-                for peer in range(W):
-                    wqkv = self._peer_view(peer, li, "wqkv")
-                    _merged(at.q_proj, wqkv[:nq])
-                    _merged(at.k_proj, wqkv[nq:nq + nkv])
-                    _merged(at.v_proj, wqkv[nq + nkv:])
-                    _merged(at.o_proj, self._peer_view(peer, li, "wo"))
-                    wgu = self._peer_view(peer, li, "wgu")
-                    _merged(mlp.gate_proj, wgu[:F])
-                    _merged(mlp.up_proj, wgu[F:])
-                    _merged(mlp.down_proj, self._peer_view(peer, li, "wdown"))
+            parts = ((at.q_proj, "wqkv", slice(0, nq)), (at.k_proj, "wqkv", slice(nq, nq + nkv)), (at.v_proj, "wqkv", slice(nq + nkv, nq + 2 * nkv)),
+                     (at.o_proj, "wo", slice(None)), (mlp.gate_proj, "wgu", slice(0, F)), (mlp.up_proj, "wgu", slice(F, 2 * F)),
+                     (mlp.down_proj, "wdown", slice(None)))
+            for mod, name, rows in parts:
+                if isinstance(mod, LoraLinear):
+                    if li % W == R:                          # this rank's share of the merge work
+                        self._write(mod, li, name, rows)
+                else:
+                    getattr(lw, name)[rows].copy_(mod.weight)     # frozen everywhere: every rank already holds it
             # biases / norms are tiny and replicated: local copies
             for mod, sl in ((at.q_proj, slice(0, nq)), (at.k_proj, slice(nq, nq + nkv)), (at.v_proj, slice(nq + nkv, nq + 2 * nkv))):
                 b = _bias(mod)
                 if b is not None:
                     lw.bqkv[sl].copy_(b)
             lw.ln1, lw.ln2 = layer.input_layernorm.weight, layer.post_attention_layernorm.weight
-        self.hdl.barrier(channel=1)                         # every peer's stores have landed
+        self.hdl.barrier(channel=1)                         # every rank's (multicast) stores have landed
         for lw in s.layers:
             interleave_gate_up(lw, F)
+        self.stats["refreshes"] += 1

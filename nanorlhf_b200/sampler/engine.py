@@ -60,9 +60,13 @@ def get_native_engine(model, **kw):
     from .native_sampler import NativeSampler
     pol = getattr(model, "policy", model)
     eng = pol.__dict__.get("_nrl_sampler")
+    comm = kw.pop("weight_sync_comm", None)
     if eng is None or eng.rollout_dtype != kw.get("rollout_dtype", eng.rollout_dtype):
         eng = NativeSampler(model, **kw)
         pol.__dict__["_nrl_sampler"] = eng        # plain attribute: not a sub-module, not in state_dict
+        if comm is not None and comm.world_size > 1:
+            from ..parallel.weight_sync import ShardedWeightSync
+            eng.sharded_sync = ShardedWeightSync(eng, comm)       # collective: every rank builds its engine at the same point
     return eng
 
 

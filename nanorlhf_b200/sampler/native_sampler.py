@@ -58,6 +58,8 @@ class NativeSampler:
         self.prefill_token_budget = prefill_token_budget
         self.sync_every = sync_every
         self.use_cuda_graph = use_cuda_graph
+        self.sharded_sync = None                        # parallel.weight_sync.ShardedWeightSync under fused data parallelism
+        self.enable_compaction = True                   # drop finished rows at sync points (tests switch it off for A/B)
         self.layers: List[_LayerWeights] = []
         self._weights_version = None
         self.k_cache: List[torch.Tensor] = []
@@ -121,7 +123,10 @@ class NativeSampler:
         ver = self.weights_fingerprint()
         if not force and self._weights_version == ver:
             return
-        refresh_sampler_arena(self)
+        if self.sharded_sync is not None:
+            self.sharded_sync.refresh()          # K-BC: layer-sharded merge, multimem.st into every rank's arena
+        else:
+            refresh_sampler_arena(self)
         if self.rollout_dtype == "fp8":
             self.quantize_arena()
         self._weights_version = ver
@@ -475,7 +480,7 @@ class NativeSampler:
                 # smaller graph bucket (the reference's vLLM does the same every step; here every sync point).
                 live = len(running) - n_fin
                 bucket = max(128, (live + 127) // 128 * 128) if self.use_cuda_graph else live
-                if sched.num_waiting() > 0 or bucket < st["S"]:
+                if sched.num_waiting() > 0 or (self.enable_compaction and bucket < st["S"]):
                     done_rows = fin.nonzero().squeeze(1).tolist()
                     self._flush_rows(st, running, out, max_tokens, n)
                     sched.finish([running[i] for i in done_rows])

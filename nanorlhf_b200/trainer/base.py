@@ -107,6 +107,13 @@ class RLTrainer:
             p.requires_grad_(False)
         self.tiering = TieringEngine(self.device)
         self.tiering.register("ref", ref_policy, args.role_residency("ref"))
+        # a model-based reward callback (reward/model_reward.py) joins the tiering engine as the "reward" role, so
+        # ``offload_reward="host"`` parks the reward model in pinned host memory between reward phases (reference:
+        # reward_model.to('cuda') / .to('cpu') around every call, GRPO/grpo.py:164,195)
+        rm = getattr(reward_func, "rm", None)
+        if isinstance(rm, nn.Module) and getattr(reward_func, "tiering", None) is None and next(rm.parameters()).device.type == self.device.type:
+            self.tiering.register("reward", rm, args.role_residency("reward"))
+            reward_func.tiering = self.tiering
         if args.gradient_checkpointing:
             policy.gradient_checkpointing_enable(args.gradient_checkpointing_kwargs)
             if self.model.value_model is not None:
@@ -187,8 +194,16 @@ class RLTrainer:
                                             a.temperature, a.response_length, top_p=a.top_p,
                                             seed=seed + self.comm.rank * 7919, backend=a.sampler,
                                             rollout_dtype=a.rollout_dtype, kv_block_size=a.kv_block_size,
-                                            kv_cache_dtype=a.kv_cache_dtype)
+                                            kv_cache_dtype=a.kv_cache_dtype, **self._weight_sync_kw())
         return {"responses": responses}
+
+    def _weight_sync_kw(self) -> dict:
+        """``weight_sync="sharded"`` (default under fused DP on CUDA): the sampler arena refresh is K-BC across ranks."""
+        a = self.args
+        if (self.comm.world_size > 1 and self.device.type == "cuda" and a.comm == "fused" and a.weight_sync != "local"
+                and a.sampler != "torch" and hasattr(self.policy, "peft_config")):
+            return {"weight_sync_comm": self.comm}
+        return {}
 
     def score(self, queries: torch.Tensor, responses: torch.Tensor) -> torch.Tensor:
         """Call the user reward callback exactly as the reference does (strings in, FloatTensor out)."""

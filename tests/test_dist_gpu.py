@@ -20,3 +20,15 @@ def test_fused_allreduce_adam_matches_nccl():
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     res = json.load(open(os.path.join(ROOT, "gpurun_out", f"dist_check_{n}.json")))
     assert res["adam_p2p_ranks_identical"]
+
+
+def test_sharded_multicast_weight_sync_matches_local_merge():
+    """K-BC: layer-sharded LoRA merge with multimem.st into every rank's sampler arena == the local merge, bit for bit."""
+    n = min(torch.cuda.device_count(), 8)
+    n = 1 << (n.bit_length() - 1)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
+                        "--master-addr", "127.0.0.1", "--master-port", "29519", os.path.join(ROOT, "bench", "dist_check_wsync.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    res = json.load(open(os.path.join(ROOT, "gpurun_out", f"wsync_check_{n}.json")))
+    assert res["identical_to_local_merge"]

@@ -77,3 +77,34 @@ def test_waves_under_kv_pressure_match_unconstrained():
     capped = NativeSampler(m, kv_cache_gb=1.0, sync_every=4, max_num_seqs=6)
     capped.sync_weights()
     assert torch.equal(capped.generate(prompts, 2, 0.0, 1.0, 40, eos, 2047, 1), want)
+
+
+def test_compaction_on_eos_heavy_batch():
+    """Finished rows leave the batch at sync points: with a 64-token vocabulary a sequence meets EOS
+    after ~64 tokens on average, far before max_tokens.  Compaction must (a) happen, (b) cut the row-steps executed, and
+    (c) leave every sampled token unchanged -- the per-row RNG stream is (seed, sequence id, tokens generated), so the
+    batch composition must not matter."""
+    from nanorlhf_b200.models.qwen2 import Qwen2Config, Qwen2ForCausalLM
+    from nanorlhf_b200.sampler.native_sampler import NativeSampler
+    cfg = Qwen2Config(vocab_size=64, hidden_size=256, intermediate_size=512, num_hidden_layers=2,
+                      num_attention_heads=2, num_key_value_heads=1, head_dim=128, tie_word_embeddings=True)
+    m = Qwen2ForCausalLM.from_config(cfg, torch.bfloat16, "cuda", seed=5)
+    g = torch.Generator().manual_seed(1)
+    prompts = [torch.randint(0, 60, (int(L),), generator=g).tolist() for L in torch.randint(4, 40, (96,), generator=g)]
+    eos, pad, max_tokens = 62, 63, 320
+    outs, stats = {}, {}
+    for compact in (False, True):
+        eng = NativeSampler(m, kv_cache_gb=1.0, sync_every=8)
+        eng.enable_compaction = compact
+        eng.sync_weights()
+        outs[compact] = eng.generate(prompts, 4, 1.0, 1.0, max_tokens, eos, pad, 7)
+        stats[compact] = dict(eng.stats)
+    a, b = outs[False], outs[True]
+    assert torch.equal(a, b), "compaction changed sampled tokens"
+    has_eos = (b == eos).any(1)
+    assert has_eos.float().mean() > 0.9                              # EOS-heavy as intended
+    first = torch.where(has_eos, (b == eos).int().argmax(1), torch.full_like(b[:, 0], max_tokens))
+    col = torch.arange(max_tokens, device=b.device)[None]
+    assert ((b == pad) | (col <= first[:, None])).all()              # nothing but padding after EOS
+    assert stats[True]["compactions"] > 0 and stats[False]["compactions"] == 0
+    assert stats[True]["row_steps"] < 0.7 * stats[False]["row_steps"], (stats[True]["row_steps"], stats[False]["row_steps"])
