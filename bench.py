@@ -49,7 +49,9 @@ def parse():
     ap.add_argument("--model", default="1.5b", choices=["tiny", "1.5b", "7b"])
     ap.add_argument("--comm", default="fused", choices=["fused", "nccl"])
     ap.add_argument("--rollout-dtype", default="bf16")
-    ap.add_argument("--kv-dtype", default="bf16", choices=["bf16", "fp8"], help="sampler KV pages (fp8 = e4m3 + per-token scales)")
+    ap.add_argument("--kv-dtype", default="fp8", choices=["bf16", "fp8"],
+                    help="sampler KV pages: fp8 = e4m3 + per-token scales (the engine's default; every GEMM and the whole training / "
+                         "log-prob / reward math stay bf16), bf16 = the round-1 setting")
     ap.add_argument("--reward", default="deberta-large", choices=["deberta-large", "deberta-tiny"])
     ap.add_argument("--grad-checkpointing", type=int, default=0,
                     help="1 = recompute activations like the reference (A100-40G memory saver); 0 = keep them (B200: 180 GB)")
@@ -166,11 +168,12 @@ def main():
     comm.barrier()
     dev_ms = ev0.elapsed_time(ev1)
     clock_info = clocks.stop() if comm.is_main else None
-    comm_ms = trainer.optimizer.pop_comm_ms() / max(1, trainer.optimizer._step - opt_steps0)
-    times = torch.tensor([dev_ms, (t1 - t0) * 1e3, comm_ms] + [phase.get(k, 0.0) for k in sorted(phase)], dtype=torch.float64, device=dev)
+    n_opt = max(1, trainer.optimizer._step - opt_steps0)
+    comm_ms, wait_ms = (x / n_opt for x in trainer.optimizer.pop_comm_ms(split=True))
+    times = torch.tensor([dev_ms, (t1 - t0) * 1e3, comm_ms, wait_ms] + [phase.get(k, 0.0) for k in sorted(phase)], dtype=torch.float64, device=dev)
     comm.all_reduce_(times, "max")
-    dev_ms, wall_ms, comm_ms = times.tolist()[:3]
-    phase = dict(zip(sorted(phase), times.tolist()[3:]))          # max over ranks, like the headline
+    dev_ms, wall_ms, comm_ms, wait_ms = times.tolist()[:4]
+    phase = dict(zip(sorted(phase), times.tolist()[4:]))          # max over ranks, like the headline
     episodes = prompts_per_rank * comm.world_size * args.steps
     value = episodes / (dev_ms / 1e3)
     e2e = episodes / (wall_ms / 1e3)
@@ -203,6 +206,9 @@ def main():
             # device time of the gradient collective per optimizer step (K-AR kernel + its two barriers; runs after the
             # last micro-step's backward, so all of it is exposed), max over ranks; 0 on one GPU
             "exposed_comm_ms_per_step": comm_ms,
+            # time a rank spends in the opening barrier of K-AR waiting for the slowest rank's backward (data-dependent load
+            # imbalance of the whole update surfaces at its first optimizer step); max over ranks; not communication
+            "straggler_wait_ms_per_step": wait_ms,
             "optimizer_steps_per_update": args.mini_batches,
         }
         print(json.dumps(line), flush=True)

@@ -63,7 +63,9 @@ class RLConfig:
     missing_eos_penalty: Optional[float] = None
     changing_seed: bool = True                  # seed=random.randint(1,5000) per rollout (:127)
     rollout_dtype: str = "bf16"                 # sampler GEMMs: bf16 | fp8 (e4m3, per-token x per-channel scales)
-    kv_cache_dtype: str = "bf16"                # sampler KV pages: bf16 | fp8 (e4m3 + per-token scales; 2x capacity)
+    kv_cache_dtype: str = "fp8"                 # sampler KV pages: fp8 (e4m3 + per-token scales: half the bytes of the HBM-bound
+                                                # decode attention, 1.6x faster, 2x capacity) | bf16.  Old log-probs are always
+                                                # recomputed by the bf16 training engine, so this only shapes the samples.
     sampler: str = "auto"                       # auto | native | torch
     kv_block_size: int = 16
 
@@ -112,6 +114,7 @@ class RLConfig:
     save_steps: int = 1
     save_total_limit: Optional[int] = 8
     save_only_model: bool = False
+    async_checkpoint: bool = True               # CUDA: snapshot to pinned host memory on a side stream, serialise in a background thread
     save_value_model: bool = True
     logging_steps: int = 1
     metric_for_best_model: str = "eval_objective/rlhf_reward_old"

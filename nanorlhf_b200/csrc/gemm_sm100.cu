@@ -326,31 +326,45 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               store_buf ^= 1;
             }
           } else if (EPI == EPI_MERGE && p.mc_out != nullptr) {
-            // ---- K-BC: W' = W + s B A straight into EVERY rank's sampler arena: one multimem.st per 16 bytes, the
-            //      NVSwitch replicates it (no per-peer recompute, no NCCL broadcast) ----
-            if (row_ok) {
-              __nv_bfloat16* mrow = p.mc_out + static_cast<long>(row) * p.mc_stride + col0;
-              const __nv_bfloat16* wrow = p.addend + static_cast<long>(row) * p.addend_stride + col0;
+            // ---- K-BC: W' = W + s B A straight into EVERY rank's sampler arena with multimem.st (the NVSwitch replicates
+            //      each store; no per-peer recompute, no NCCL broadcast).  The tile is staged through shared memory so that
+            //      a warp writes four full 128-byte row segments per instruction instead of 32 scattered 16-byte pieces ----
+            uint8_t* buf = staging + store_buf * kStagingBytes;
+            named_barrier_sync(1, kNumEpiThreads);            // the previous chunk's readers are done with `buf`
+            {
+              uint32_t packed[32];
 #pragma unroll
               for (int h = 0; h < 2; ++h)
 #pragma unroll
-                for (int j = 0; j < 32; j += 8) {
+                for (int j = 0; j < 32; j += 2) {
+                  float x0 = __uint_as_float(v[h][j]) * p.scale, x1 = __uint_as_float(v[h][j + 1]) * p.scale;
                   const int col = col0 + h * 32 + j;
-                  if (col < p.N) {                      // N % 8 == 0 (checked on the host)
-                    const uint4 w8 = *reinterpret_cast<const uint4*>(wrow + h * 32 + j);
-                    const uint32_t ww[4] = {w8.x, w8.y, w8.z, w8.w};
-                    uint32_t o[4];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                      const float2 w2 = unpack_bf16x2(ww[q]);
-                      o[q] = pack_bf16x2(__uint_as_float(v[h][j + 2 * q]) * p.scale + w2.x,
-                                         __uint_as_float(v[h][j + 2 * q + 1]) * p.scale + w2.y);
-                    }
-                    asm volatile("multimem.st.relaxed.sys.global.v4.bf16x2 [%0], {%1,%2,%3,%4};"
-                                 ::"l"(mrow + h * 32 + j), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+                  if (row_ok && col + 1 < p.N) {
+                    const float2 w2 = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(p.addend + static_cast<long>(row) * p.addend_stride + col));
+                    x0 += w2.x;
+                    x1 += w2.y;
                   }
+                  packed[h * 16 + j / 2] = pack_bf16x2(x0, x1);
                 }
+              uint8_t* rowp = buf + row_in_tile * 128;
+#pragma unroll
+              for (int ch = 0; ch < 8; ++ch)
+                *reinterpret_cast<uint4*>(rowp + ((ch ^ (row_in_tile & 7)) * 16)) =
+                    make_uint4(packed[ch * 4], packed[ch * 4 + 1], packed[ch * 4 + 2], packed[ch * 4 + 3]);
             }
+            named_barrier_sync(2, kNumEpiThreads);
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int idx = it * kNumEpiThreads + epi_tid;  // 1024 16-byte pieces: piece = (row r, chunk ch)
+              const int r = idx >> 3, ch = idx & 7;
+              const int grow = m_blk * BLOCK_M + r, gcol = col0 + ch * 8;
+              if (grow < p.M && gcol < p.N) {                 // N % 8 == 0 (checked on the host)
+                const uint4 q = *reinterpret_cast<const uint4*>(buf + r * 128 + ((ch ^ (r & 7)) * 16));
+                asm volatile("multimem.st.relaxed.sys.global.v4.bf16x2 [%0], {%1,%2,%3,%4};"
+                             ::"l"(p.mc_out + static_cast<long>(grow) * p.mc_stride + gcol), "r"(q.x), "r"(q.y), "r"(q.z), "r"(q.w) : "memory");
+              }
+            }
+            store_buf ^= 1;
           } else {
             // ---- bf16 tile store through swizzled smem + TMA ----
             uint8_t* buf = staging + store_buf * kStagingBytes;

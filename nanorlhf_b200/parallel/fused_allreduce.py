@@ -26,6 +26,7 @@ class FusedAllReduceAdam:
         self.max_blocks = max_blocks
         self.use_multicast = os.environ.get("NANORLHF_NVLS", use_multicast)
         self.bytes_reduced = 0
+        self.wait_events = []      # (start, end) around the opening barrier of every K-AR step: time spent waiting for the slowest rank
         native.load()
 
     def alloc(self, n: int, dtype: torch.dtype, device) -> torch.Tensor:
@@ -60,13 +61,25 @@ class FusedAllReduceAdam:
         n = hi - lo
         mc_g, mc_p = self._mc(gh), self._mc(ph)
         use_mc = bool(mc_g and mc_p)
+        w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0.record()
         gh.barrier(channel=0)                      # every rank's backward has finished writing its gradients
+        w1.record()
+        self.wait_events.append((w0, w1))
         native._count()
         native.ext().allreduce_adam(list(gh.buffer_ptrs), list(ph.buffer_ptrs), mc_g, mc_p, f.exp_avg, f.exp_avg_sq,
                                     lo, n, rank, hp["lr"], hp["beta1"], hp["beta2"], hp["eps"], hp["wd"], hp["step"],
                                     scale, use_mc, self.max_blocks, getattr(f, "master", None))
         ph.barrier(channel=1)                      # updated parameters are visible on every rank
         self.bytes_reduced += f.padded * f.grad.element_size()
+
+    def pop_wait_ms(self) -> float:
+        ms = 0.0
+        for a, b in self.wait_events:
+            b.synchronize()
+            ms += a.elapsed_time(b)
+        self.wait_events.clear()
+        return ms
 
     @torch.no_grad()
     def allreduce_(self, t: torch.Tensor, scale: float = 1.0):

@@ -206,15 +206,18 @@ class FusedAdamW(torch.optim.Optimizer):
                 self.comm_events.append((ev0, ev1))
         return None
 
-    def pop_comm_ms(self) -> float:
-        """Device time spent in step()'s collectives since the last call (K-AR: the fused kernel + its two
-        barriers -- all of it is exposed, nothing overlaps it).  Synchronises on the recorded events."""
+    def pop_comm_ms(self, split: bool = False):
+        """Device time spent in step()'s collectives since the last call.  For K-AR that is the opening barrier (= waiting
+        for the slowest rank to finish its backward: load imbalance, not communication), the fused kernel and the closing
+        barrier; nothing overlaps it, so all of it is exposed.  ``split=True`` returns (communication, straggler wait).
+        Synchronises on the recorded events."""
         ms = 0.0
         for a, b in self.comm_events:
             b.synchronize()
             ms += a.elapsed_time(b)
         self.comm_events.clear()
-        return ms
+        wait = self._fused.pop_wait_ms() if self._fused is not None else 0.0
+        return (ms - wait, wait) if split else ms
 
     def grad_norm(self) -> torch.Tensor:
         sq = sum((f.grad.float() ** 2).sum() for f in self.flats)

@@ -32,18 +32,113 @@ PREFIX = "checkpoint"
 _RE = re.compile(rf"^{PREFIX}-(\d+)$")
 
 
-def _save_one_model(model, path: str):
+class AsyncCheckpointWriter:
+    """Saving every update (the reference's ``save_steps=1``) must not stall the GPU: device tensors are snapshotted into
+    reusable pinned host buffers by ``cudaMemcpyAsync`` on a side stream, and a background thread serialises them
+    (safetensors / torch.save) once the copy event has fired -- the next update's rollout overlaps both.  The trainer
+    calls ``wait_snapshot()`` before its next optimizer step (the only point where the snapshotted tensors change) and
+    ``wait()`` before the next checkpoint / at the end of training."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.cuda = self.device.type == "cuda"
+        self.stream = torch.cuda.Stream(self.device) if self.cuda else None
+        self.event = None
+        self.thread = None
+        self.error = None
+        self._pinned = {}
+
+    def snapshot(self, tensors: dict) -> dict:
+        """Device -> pinned-host copies of ``tensors`` (dict of name -> tensor); returns host views valid after the event."""
+        out = {}
+        if not self.cuda:
+            return {k: v.detach().clone() for k, v in tensors.items()}
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.stream):
+            for k, v in tensors.items():
+                v = v.detach()
+                if v.device.type != "cuda":
+                    out[k] = v.clone()
+                    continue
+                buf = self._pinned.get(k)
+                if buf is None or buf.shape != v.shape or buf.dtype != v.dtype:
+                    buf = torch.empty(v.shape, dtype=v.dtype, pin_memory=True)
+                    self._pinned[k] = buf
+                buf.copy_(v, non_blocking=True)
+                v.record_stream(self.stream)
+                out[k] = buf
+            self.event = torch.cuda.Event()
+            self.event.record(self.stream)
+        return out
+
+    def submit(self, fn):
+        import threading
+        self.wait()
+        ev = self.event
+
+        def run():
+            try:
+                if ev is not None:
+                    ev.synchronize()
+                fn()
+            except BaseException as e:  # noqa: BLE001 -- surfaced on the training thread by wait()
+                self.error = e
+
+        self.thread = threading.Thread(target=run, name="nanorlhf-ckpt-writer", daemon=False)
+        self.thread.start()
+
+    def wait_snapshot(self):
+        if self.event is not None:
+            self.event.synchronize()
+
+    def wait(self):
+        if self.thread is not None:
+            self.thread.join()
+            self.thread = None
+        if self.error is not None:
+            e, self.error = self.error, None
+            raise RuntimeError("asynchronous checkpoint write failed") from e
+
+
+def _model_tensors(model) -> dict:
+    """The tensors ``save_pretrained`` would write: the peft adapter state dict, or the full state dict."""
+    if hasattr(model, "adapter_state_dict"):
+        return dict(model.adapter_state_dict())
+    sd = dict(model.state_dict())
+    if getattr(model.config, "tie_word_embeddings", False):
+        sd.pop("lm_head.weight", None)
+    return sd
+
+
+def _save_one_model(model, path: str, host_state: Optional[dict] = None):
+    """``host_state``: pre-fetched (pinned host) copies of ``_model_tensors(model)`` -- the async writer's path."""
     os.makedirs(path, exist_ok=True)
-    model.save_pretrained(path)
+    if host_state is None:
+        model.save_pretrained(path)
+        return
+    import json
+    from dataclasses import asdict
+    from ..models.hf_io import save_state_dict
+    if hasattr(model, "adapter_state_dict"):
+        cfg = asdict(model.peft_config)
+        cfg["base_model_name_or_path"] = getattr(model, "name_or_path", "")
+        with open(os.path.join(path, "adapter_config.json"), "w") as f:
+            json.dump(cfg, f, indent=2)
+        save_state_dict(host_state, os.path.join(path, "adapter_model.safetensors"))
+    else:
+        with open(os.path.join(path, "config.json"), "w") as f:
+            json.dump(model.config.to_dict(), f, indent=2)
+        save_state_dict(host_state, os.path.join(path, "model.safetensors"))
 
 
-def save_model(trainer, output_dir: str):
+def save_model(trainer, output_dir: str, host_states: Optional[dict] = None):
     """Policy only (adapter when LoRA), + ``value_model/`` for PPO, + tokenizer + training_args.bin."""
     if not trainer.comm.is_main:
         return
-    _save_one_model(trainer.policy, output_dir)
+    hs = host_states or {}
+    _save_one_model(trainer.policy, output_dir, hs.get("policy"))
     if trainer.uses_value_model and trainer.args.save_value_model and trainer.model.value_model is not None:
-        _save_one_model(trainer.model.value_model, os.path.join(output_dir, "value_model"))
+        _save_one_model(trainer.model.value_model, os.path.join(output_dir, "value_model"), hs.get("value"))
     if hasattr(trainer.tokenizer, "save_pretrained"):
         trainer.tokenizer.save_pretrained(output_dir)
     torch.save(trainer.args.to_dict(), os.path.join(output_dir, "training_args.bin"))      # torch.load-able like HF's
@@ -63,6 +158,10 @@ def save_checkpoint(trainer, metrics=None):
     if comm.is_main:
         os.makedirs(out, exist_ok=True)
     comm.barrier()
+    writer = getattr(trainer, "ckpt_writer", None)
+    use_async = bool(getattr(a, "async_checkpoint", False)) and writer is not None and trainer.device.type == "cuda"
+    if use_async:
+        return _save_checkpoint_async(trainer, writer, out, metrics)
     save_model(trainer, out)
     if not a.save_only_model:
         # one world-size independent optimizer.pt (reference layout): under fused DP the ZeRO-1 shards of the moments /
@@ -99,6 +198,71 @@ def save_checkpoint(trainer, metrics=None):
         st.save_to_json(os.path.join(out, "trainer_state.json"))
         rotate_checkpoints(a.output_dir, a.save_total_limit, st.best_model_checkpoint)
     comm.barrier()
+    return out
+
+
+def _update_best(trainer, out: str, metrics):
+    a, st = trainer.args, trainer.state
+    if metrics is not None and a.metric_for_best_model and a.metric_for_best_model in metrics:
+        name, val = a.metric_for_best_model, metrics[a.metric_for_best_model]
+        better = (lambda x, y: x > y) if a.greater_is_better else (lambda x, y: x < y)
+        if st.best_metric is None or st.best_model_checkpoint is None or better(val, st.best_metric):
+            st.best_metric = val
+            prev = os.path.join(a.output_dir, f"{PREFIX}-{st.global_step - 1}")
+            st.best_model_checkpoint = prev if (name.endswith("_old") and os.path.isdir(prev)) else out
+
+
+def _save_checkpoint_async(trainer, writer: AsyncCheckpointWriter, out: str, metrics):
+    """Same files as the synchronous path; the device -> host copies run on the writer's side stream and the serialisation
+    in its thread.  Collective parts (gathering the ZeRO-1 optimizer shards) happen here, on every rank."""
+    import copy
+    import json  # noqa: F401
+    a, st, comm = trainer.args, trainer.state, trainer.comm
+    writer.wait()                                               # one checkpoint in flight at a time
+    host = {}
+    if comm.is_main:
+        host["policy"] = writer.snapshot({f"p.{k}": v for k, v in _model_tensors(trainer.policy).items()})
+        host["policy"] = {k[2:]: v for k, v in host["policy"].items()}
+        if trainer.uses_value_model and a.save_value_model and trainer.model.value_model is not None:
+            host["value"] = {k[2:]: v for k, v in writer.snapshot({f"v.{k}": v for k, v in _model_tensors(trainer.model.value_model).items()}).items()}
+    opt_sd = None
+    if not a.save_only_model:
+        opt = trainer.optimizer
+        if hasattr(opt, "state_tensors"):
+            dev_state = {}
+            for k, v in opt.state_tensors().items():           # gather shards on the device (collective), copy asynchronously
+                f = opt._flats[int(k.split(".")[0][5:])]
+                dev_state[k] = comm.all_gather_cat(v)[:f.padded] if getattr(opt, "comm_mode", "none") == "fused" else v
+            if comm.is_main:
+                host_state = {k[2:]: v for k, v in writer.snapshot({f"o.{k}": v for k, v in dev_state.items()}).items()}
+                opt_sd = {"step": opt._step, "world": 1 if opt.comm_mode == "fused" else opt.world,
+                          "comm_mode": "full" if opt.comm_mode == "fused" else opt.comm_mode,
+                          "param_groups": [{k: v for k, v in g.items() if k != "params"} for g in opt.param_groups], "state": host_state}
+        elif comm.is_main:
+            opt_sd = opt.state_dict()
+    rng = _rng_state(trainer.device)
+    rng["sampler_seed_stream"] = sampler_engine.seed_stream_state()
+    rng["trainer_np_rng"] = trainer._np_rng.get_state()
+    rng["trainer_select_gen"] = trainer._select_gen.get_state()
+    rng["dataloader"] = trainer.dataloader.state_dict()
+    sched_sd = copy.deepcopy(trainer.lr_scheduler.state_dict())
+    _update_best(trainer, out, metrics)
+    state_snapshot = copy.deepcopy(st)
+    rank_rng_name = "rng_state.pth" if comm.world_size == 1 else f"rng_state_{comm.rank}.pth"
+
+    def write():
+        if not a.save_only_model:
+            torch.save(rng, os.path.join(out, rank_rng_name))
+        if not comm.is_main:
+            return
+        save_model(trainer, out, host)
+        if not a.save_only_model:
+            torch.save(opt_sd, os.path.join(out, "optimizer.pt"))
+            torch.save(sched_sd, os.path.join(out, "scheduler.pt"))
+        state_snapshot.save_to_json(os.path.join(out, "trainer_state.json"))     # written last: marks the checkpoint complete
+        rotate_checkpoints(a.output_dir, a.save_total_limit, state_snapshot.best_model_checkpoint)
+
+    writer.submit(write)
     return out
 
 

@@ -148,6 +148,7 @@ class RLTrainer:
         self.heartbeat = Heartbeat(os.path.join(args.output_dir, "heartbeat"), self.comm.rank,
                                    args.watchdog_timeout_s, enable_watchdog=self.comm.world_size > 1)
         self.last_completions = None
+        self.ckpt_writer = ckpt.AsyncCheckpointWriter(self.device)
         self._resumed = False
         self.io_bytes = {"h2d": 0, "d2h": 0}           # host<->device traffic of the public step API
         if self.comm.is_main:
@@ -320,6 +321,8 @@ class RLTrainer:
         if self.control.should_save:
             self._save_checkpoint(self.model, trial=None, metrics=metrics)
             self.control = self.callback_handler.on_save(a, self.state, self.control)
+        self.ckpt_writer.wait()
+        self.comm.barrier()
         self._maybe_load_best()
         self.heartbeat.close()
         return metrics
@@ -492,6 +495,7 @@ class RLTrainer:
         graphed = self._graph_micro_step()
         keys = graphed.stat_keys if graphed is not None else None
         rows = {}
+        self.ckpt_writer.wait_snapshot()          # an in-flight checkpoint has finished READING the parameters / moments
         self.policy.train()
         for ep in range(a.num_ppo_epochs):
             b_inds = self._np_rng.permutation(n_local)

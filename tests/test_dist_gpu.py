@@ -32,3 +32,15 @@ def test_sharded_multicast_weight_sync_matches_local_merge():
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     res = json.load(open(os.path.join(ROOT, "gpurun_out", f"wsync_check_{n}.json")))
     assert res["identical_to_local_merge"]
+
+
+def test_data_parallel_equivalence():
+    """T3: N ranks x batch G/N through K-AR == 1 rank accumulating batch G (same seeds), and all ranks end bit-identical."""
+    n = min(torch.cuda.device_count(), 8)
+    n = 1 << (n.bit_length() - 1)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
+                        "--master-addr", "127.0.0.1", "--master-port", "29521", os.path.join(ROOT, "bench", "dist_check_dp.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    res = json.load(open(os.path.join(ROOT, "gpurun_out", f"dp_equiv_{n}.json")))
+    assert res["ok"], res

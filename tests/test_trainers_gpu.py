@@ -115,3 +115,32 @@ def test_grpo_trains_with_cuda_graph_micro_steps(tmp_path):
         if isinstance(v, float):
             assert v == v and abs(v) < 1e9, (k, v)
     assert all(torch.isfinite(p).all() for p in t.policy.parameters())
+
+
+def test_async_checkpoint_roundtrip(tmp_path):
+    """save_steps=1 with the asynchronous writer (pinned-host snapshot on a side stream + background serialisation): every
+    checkpoint directory is complete, and the adapter / optimizer state on disk is the state AT THAT UPDATE (the snapshot
+    must not race with the next update's optimizer steps)."""
+    import nanorlhf_b200.trainer as T
+    from nanorlhf_b200.models.hf_io import load_state_dict
+    t = _setup(tmp_path, T.GRPOTrainer, {"grpo_sample_N": 4}, save_strategy="steps", save_steps=1, total_episodes=24)
+    assert t.args.async_checkpoint
+    snaps = {}
+    orig = t._save_checkpoint
+
+    def spy(model, trial=None, metrics=None):
+        snaps[t.state.global_step] = {k: v.detach().clone() for k, v in t.policy.adapter_state_dict().items()}
+        snaps[(t.state.global_step, "m")] = t.optimizer.flats[0].exp_avg.clone()
+        return orig(model, trial, metrics)
+
+    t._save_checkpoint = spy
+    t.train()
+    for step in (1, 2, 3):
+        d = os.path.join(str(tmp_path), f"checkpoint-{step}")
+        for f in ("adapter_model.safetensors", "adapter_config.json", "optimizer.pt", "scheduler.pt", "rng_state.pth", "trainer_state.json"):
+            assert os.path.exists(os.path.join(d, f)), (step, f)
+        sd = load_state_dict(os.path.join(d, "adapter_model.safetensors"))
+        for k, v in snaps[step].items():
+            assert torch.equal(sd[k].to(v.device), v), (step, k)
+        opt = torch.load(os.path.join(d, "optimizer.pt"), map_location="cpu", weights_only=False)
+        assert torch.equal(opt["state"]["group0.exp_avg"], snaps[(step, "m")].cpu())
