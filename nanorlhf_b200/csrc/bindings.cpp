@@ -367,6 +367,37 @@ torch::Tensor gemm_fp8(const torch::Tensor& aq, const torch::Tensor& a_scale, co
   return out;
 }
 
+// fp8 rollout GEMM on gemm_tc (cta_group 1 | 2): D (bf16) = (Aq Bq^T) * a_scale[M] * b_scale[N] (+bias); swiglu: interleaved Bq rows, D [M, N/2]
+torch::Tensor gemm_tc_fp8(const torch::Tensor& aq, const torch::Tensor& a_scale, const torch::Tensor& bq, const torch::Tensor& b_scale,
+                          const c10::optional<torch::Tensor>& bias, bool swiglu, int64_t cg_req, int64_t bn_req) {
+  TORCH_CHECK(aq.is_cuda() && aq.scalar_type() == torch::kUInt8 && aq.dim() == 2 && aq.stride(1) == 1 && aq.stride(0) % 16 == 0);
+  TORCH_CHECK(bq.is_cuda() && bq.scalar_type() == torch::kUInt8 && bq.dim() == 2 && bq.stride(1) == 1 && bq.stride(0) % 16 == 0);
+  const int64_t M = aq.size(0), K = aq.size(1), N = bq.size(0);
+  TORCH_CHECK(bq.size(1) == K && K % 16 == 0 && N % 8 == 0);
+  TORCH_CHECK(a_scale.scalar_type() == torch::kFloat32 && a_scale.numel() == M && b_scale.scalar_type() == torch::kFloat32 && b_scale.numel() == N);
+  c10::cuda::CUDAGuard guard(aq.device());
+  const int64_t No = swiglu ? N / 2 : N;
+  torch::Tensor out = torch::empty({M, No}, aq.options().dtype(torch::kBFloat16));
+  if (M == 0) return out;
+  TcChoice ch = pick_tc_tile(M, N, false, false, false);
+  if (ch.bn == 64) ch.bn = 128;
+  if (swiglu && ch.bn == 192) ch.bn = (N % 256 == 0) ? 256 : 128;
+  if (swiglu && N % ch.bn != 0) ch.bn = 128;
+  if (cg_req > 0) ch.cg = static_cast<int>(cg_req);
+  if (bn_req > 0) ch.bn = static_cast<int>(bn_req);
+  CUtensorMap maps[3];
+  maps[0] = nrl::make_tma_2d(aq.data_ptr(), M, K, aq.stride(0), 128, 128, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1);
+  maps[1] = nrl::make_tma_2d(bq.data_ptr(), N, K, bq.stride(0), ch.bn / ch.cg, 128, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1);
+  maps[2] = nrl::make_tma_2d(out.data_ptr(), M, No, out.stride(0) * 2, 128, 64, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2);
+  nrl::tc::TcParams p{};
+  p.M = static_cast<int>(M); p.N = static_cast<int>(N); p.K = static_cast<int>(K); p.alpha = 1.f;
+  p.row_scale = a_scale.data_ptr<float>();
+  p.col_scale = b_scale.data_ptr<float>();
+  if (bias.has_value()) p.bias = reinterpret_cast<const __nv_bfloat16*>(bias->data_ptr());
+  check(nrl_gemm_tc_fp8(maps, &p, ch.cg, ch.bn, swiglu ? 1 : 0, num_sms(), cur_stream()), "gemm_tc_fp8");
+  return out;
+}
+
 int pick_splits(int64_t M, int64_t N, int bn) {
   int64_t num_m = (M + 127) / 128, num_n = (N + bn - 1) / bn;
   int64_t s = (num_sms() + num_m - 1) / num_m;       // enough work items to cover the SMs
@@ -935,6 +966,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("b2") = py::none(), py::arg("bias") = py::none(), py::arg("act") = 0, py::arg("alpha") = 1.0, py::arg("out") = py::none(),
         py::arg("out_f32") = py::none(), py::arg("accumulate") = false, py::arg("cg") = 0, py::arg("block_n") = 0,
         py::arg("split_k") = -1);      // -1 = automatic, 0 = never, n = exactly n k-ranges
+  m.def("gemm_tc_fp8", &gemm_tc_fp8, py::arg("aq"), py::arg("a_scale"), py::arg("bq"), py::arg("b_scale"), py::arg("bias") = py::none(),
+        py::arg("swiglu") = false, py::arg("cg") = 0, py::arg("block_n") = 0);
   m.def("gemm_tc_batched", &gemm_tc_batched, py::arg("a"), py::arg("b"), py::arg("out") = py::none(), py::arg("cg") = 0, py::arg("block_n") = 0);
   m.def("gemm_tc_swiglu", &gemm_tc_swiglu, py::arg("a"), py::arg("w_interleaved"), py::arg("out") = py::none(), py::arg("cg") = 0,
         py::arg("block_n") = 0);

@@ -96,6 +96,18 @@ NRL_DEVICE void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uin
                  ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
   }
 }
+template <int CG>
+NRL_DEVICE void umma_fp8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  if (CG == 1) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}\n"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+  } else {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}\n"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+  }
+}
 // all MMAs issued so far by this thread arrive on `bar` when they retire (CG = 2: on the barrier at the same offset in
 // BOTH CTAs of the pair)
 template <int CG>
@@ -165,7 +177,10 @@ NRL_DEVICE void tma_store_3d(const CUtensorMap* m, const void* smem_src, int c0,
                ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
-template <int CG, int BN, bool A_MN, bool B_MN, int EPI, bool SPLIT = false, bool BATCH = false>
+// FP8: A and B are e4m3 bytes, K-major (a 128-byte swizzle row = 128 contraction elements), the MMA is kind::f8f6f4
+// (K = 32 per instruction, twice the bf16 rate) and the epilogue applies the per-row (token) and per-column (output
+// channel) dequantisation scales -- the sampler's fp8 rollout GEMMs (north star: fp8 tcgen05 GEMM in the decoder).
+template <int CG, int BN, bool A_MN, bool B_MN, int EPI, bool SPLIT = false, bool BATCH = false, bool FP8 = false>
 NRL_DEVICE void gemm_tc_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmA2, const CUtensorMap& tmB2,
                              const CUtensorMap& tmD, const TcParams& p) {
   using C = Cfg<CG, BN, B_MN>;
@@ -181,8 +196,9 @@ NRL_DEVICE void gemm_tc_body(const CUtensorMap& tmA, const CUtensorMap& tmB, con
   const bool leader = rank == 0;
   const int num_m = (p.M + CG * BLOCK_M - 1) / (CG * BLOCK_M);
   const int num_n = (p.N + BN - 1) / BN;
-  const int num_kb1 = (p.K + BLOCK_K - 1) / BLOCK_K;
-  const int num_kb = num_kb1 + (p.K2 + BLOCK_K - 1) / BLOCK_K;
+  constexpr int kElemsPerKB = FP8 ? 2 * BLOCK_K : BLOCK_K;                  // 128 bytes of contraction per k-block either way
+  const int num_kb1 = (p.K + kElemsPerKB - 1) / kElemsPerKB;
+  const int num_kb = num_kb1 + (p.K2 + kElemsPerKB - 1) / kElemsPerKB;
   const int splits = SPLIT ? p.splits : 1;
   const int kb_per_split = (num_kb + splits - 1) / splits;
   const int tiles_per_batch = num_m * num_n;
@@ -240,7 +256,7 @@ NRL_DEVICE void gemm_tc_body(const CUtensorMap& tmA, const CUtensorMap& tmB, con
           const bool second = kb >= num_kb1;
           const CUtensorMap* ma = second ? &tmA2 : &tmA;
           const CUtensorMap* mb = second ? &tmB2 : &tmB;
-          const int k0 = (second ? kb - num_kb1 : kb) * BLOCK_K;
+          const int k0 = (second ? kb - num_kb1 : kb) * kElemsPerKB;
           if (BATCH) {
             tma_load3_cg<CG>(sa, ma, &full_bar[stage], k0, m0, bidx);
             tma_load3_cg<CG>(sb, mb, &full_bar[stage], k0, n0, bidx);
@@ -267,7 +283,8 @@ NRL_DEVICE void gemm_tc_body(const CUtensorMap& tmA, const CUtensorMap& tmB, con
   } else if (warp == 1) {
     // ================================ MMA issuer (leader CTA only) ================================
     if (leader && elect_one()) {
-      constexpr uint32_t idesc = make_idesc_tc(CG * BLOCK_M, BN, A_MN, B_MN);
+      constexpr uint32_t idesc = FP8 ? ((1u << 4) | ((static_cast<uint32_t>(BN) >> 3) << 17) | ((static_cast<uint32_t>(CG * BLOCK_M) >> 4) << 24))
+                                     : make_idesc_tc(CG * BLOCK_M, BN, A_MN, B_MN);          // e4m3 x e4m3 (format code 0) -> fp32
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -289,7 +306,8 @@ NRL_DEVICE void gemm_tc_body(const CUtensorMap& tmA, const CUtensorMap& tmB, con
                                         : make_smem_desc_sw128(a_addr + k * UMMA_K * 2);
             const uint64_t bdesc = B_MN ? make_smem_desc_sw128_mn(b_addr + k * UMMA_K * 128, kPanelBytes)
                                         : make_smem_desc_sw128(b_addr + k * UMMA_K * 2);
-            umma_bf16<CG>(d_tmem, adesc, bdesc, idesc, ((kb - kb_lo) | k) != 0 ? 1u : 0u);
+            if (FP8) umma_fp8<CG>(d_tmem, adesc, bdesc, idesc, ((kb - kb_lo) | k) != 0 ? 1u : 0u);
+            else umma_bf16<CG>(d_tmem, adesc, bdesc, idesc, ((kb - kb_lo) | k) != 0 ? 1u : 0u);
           }
           umma_commit_cg<CG>(&empty_bar[stage]);        // smem stage reusable once these MMAs retire
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
@@ -412,10 +430,16 @@ NRL_DEVICE void gemm_tc_body(const CUtensorMap& tmA, const CUtensorMap& tmB, con
           // weight-refresh time, parallel/weight_sync.py): silu(g) * u is formed in registers, two chunks make one 64-wide
           // output slab -- the [tokens, 2F] gate_up tensor never exists
           constexpr float kLog2e = 1.4426950408889634f;
+          const float rs8 = (FP8 && row_ok) ? p.row_scale[row] : 1.f;
 #pragma unroll
           for (int j = 0; j < 32; j += 2) {
-            const float g0 = __uint_as_float(v[0][j]), g1 = __uint_as_float(v[0][j + 1]);
-            const float u0 = __uint_as_float(v[1][j]), u1 = __uint_as_float(v[1][j + 1]);
+            float g0 = __uint_as_float(v[0][j]), g1 = __uint_as_float(v[0][j + 1]);
+            float u0 = __uint_as_float(v[1][j]), u1 = __uint_as_float(v[1][j + 1]);
+            if (FP8) {
+              const int cg_ = min(col0 + j, p.N - 2), cu_ = min(col0 + 32 + j, p.N - 2);
+              g0 *= rs8 * p.col_scale[cg_]; g1 *= rs8 * p.col_scale[cg_ + 1];
+              u0 *= rs8 * p.col_scale[cu_]; u1 *= rs8 * p.col_scale[cu_ + 1];
+            }
             const uint32_t pk = pack_bf16x2(g0 / (1.f + exp2f(-g0 * kLog2e)) * u0, g1 / (1.f + exp2f(-g1 * kLog2e)) * u1);
             if ((ch & 1) == 0) sw_packed[j / 2] = pk;     // static indices: the array stays in registers
             else sw_packed[16 + j / 2] = pk;
@@ -448,6 +472,11 @@ NRL_DEVICE void gemm_tc_body(const CUtensorMap& tmA, const CUtensorMap& tmB, con
             for (int j = 0; j < 32; j += 2) {
               float x0 = __uint_as_float(v[h][j]) * p.alpha, x1 = __uint_as_float(v[h][j + 1]) * p.alpha;
               const int col = col0 + h * 32 + j;
+              if (FP8) {
+                const float rs = row_ok ? p.row_scale[row] : 0.f;
+                x0 *= rs * ((col < p.N) ? p.col_scale[col] : 0.f);
+                x1 *= rs * ((col + 1 < p.N) ? p.col_scale[col + 1] : 0.f);
+              }
               if (p.bias != nullptr) {
                 if (col < p.N) x0 += __bfloat162float(p.bias[col]);
                 if (col + 1 < p.N) x1 += __bfloat162float(p.bias[col + 1]);
@@ -514,6 +543,46 @@ gemm_tc_batched_cg2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
                            const __grid_constant__ CUtensorMap tmD, const TcParams p) {
   gemm_tc_body<2, BN, false, false, EPI_BF16, false, true>(tmA, tmB, tmA, tmB, tmD, p);
 }
+template <int BN, int EPI>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tc_fp8_cg1_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                       const __grid_constant__ CUtensorMap tmD, const TcParams p) {
+  gemm_tc_body<1, BN, false, false, EPI, false, false, true>(tmA, tmB, tmA, tmB, tmD, p);
+}
+template <int BN, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm_tc_fp8_cg2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                       const __grid_constant__ CUtensorMap tmD, const TcParams p) {
+  gemm_tc_body<2, BN, false, false, EPI, false, false, true>(tmA, tmB, tmA, tmB, tmD, p);
+}
+template <int CG, int BN, int EPI>
+static cudaError_t launch_fp8(const CUtensorMap* maps, const TcParams& p, int num_sms, cudaStream_t stream) {
+  using C = Cfg<CG, BN, false>;
+  const int num_m = (p.M + CG * BLOCK_M - 1) / (CG * BLOCK_M), num_n = (p.N + BN - 1) / BN;
+  int units = num_m * num_n;
+  if (units > num_sms / CG) units = num_sms / CG;
+  if (units < 1) units = 1;
+  static bool configured = false;
+  if (CG == 1) {
+    auto kern = gemm_tc_fp8_cg1_kernel<BN, EPI>;
+    if (!configured) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kTotal);
+      if (e != cudaSuccess) return e;
+      configured = true;
+    }
+    kern<<<units, kThreads, C::kTotal, stream>>>(maps[0], maps[1], maps[2], p);
+  } else {
+    auto kern = gemm_tc_fp8_cg2_kernel<BN, EPI>;
+    if (!configured) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kTotal);
+      if (e != cudaSuccess) return e;
+      configured = true;
+    }
+    kern<<<2 * units, kThreads, C::kTotal, stream>>>(maps[0], maps[1], maps[2], p);
+  }
+  return cudaGetLastError();
+}
+
 template <int CG, int BN>
 static cudaError_t launch_batched(const CUtensorMap* maps, const TcParams& p, int num_sms, cudaStream_t stream) {
   using C = Cfg<CG, BN, false>;
@@ -595,6 +664,24 @@ static cudaError_t launch(const CUtensorMap* maps, const TcParams& p, int num_sm
 
 }  // namespace tc
 }  // namespace nrl
+
+// e4m3 x e4m3 GEMM with per-row x per-column scales; maps = {A (uint8 [M,K], box {128, 128}), B (uint8 [N,K], box {bn/cg, 128}), D}
+extern "C" cudaError_t nrl_gemm_tc_fp8(const CUtensorMap* maps, const nrl::tc::TcParams* p, int cg, int bn, int swiglu, int num_sms,
+                                       cudaStream_t stream) {
+  using namespace nrl::tc;
+  if (p->row_scale == nullptr || p->col_scale == nullptr || p->K2 != 0) return cudaErrorInvalidValue;
+#define NRL_TC_FP8(CG_, BN_)                                                                                     \
+  if (cg == CG_ && bn == BN_)                                                                                    \
+    return swiglu ? launch_fp8<CG_, BN_, EPI_SWIGLU>(maps, *p, num_sms, stream) : launch_fp8<CG_, BN_, EPI_BF16>(maps, *p, num_sms, stream);
+  NRL_TC_FP8(1, 128)
+  NRL_TC_FP8(1, 256)
+  NRL_TC_FP8(2, 128)
+  NRL_TC_FP8(2, 256)
+#undef NRL_TC_FP8
+  if (!swiglu && cg == 2 && bn == 192) return launch_fp8<2, 192, EPI_BF16>(maps, *p, num_sms, stream);
+  if (!swiglu && cg == 1 && bn == 192) return launch_fp8<1, 192, EPI_BF16>(maps, *p, num_sms, stream);
+  return cudaErrorInvalidValue;
+}
 
 extern "C" cudaError_t nrl_gemm_tc_batched(const CUtensorMap* maps, const nrl::tc::TcParams* p, int cg, int bn, int num_sms,
                                            cudaStream_t stream) {

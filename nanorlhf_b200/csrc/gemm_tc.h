@@ -16,6 +16,8 @@ enum TcEpilogue : int {
 struct TcParams {
   int M, N, K;                  // D is [M, N]; K = contraction length of the first operand pair
   int K2;                       // contraction length of the second operand pair (0 = none)
+  const float* row_scale;       // FP8 kernels: [M] per-token dequantisation scale of A
+  const float* col_scale;       // FP8 kernels: [N] per-output-channel dequantisation scale of B
   int batch;                    // BATCH kernels: number of independent [M,K] x [N,K]^T problems behind 3D tensor maps (else 1)
   float alpha;                  // multiplies the accumulator
   const __nv_bfloat16* bias;    // EPI_BF16: optional [N]
@@ -38,6 +40,8 @@ struct TcParams {
 
 extern "C" cudaError_t nrl_gemm_tc_splitk(const CUtensorMap* maps, const nrl::tc::TcParams* p, int bn, int a_mn, int b_mn, int num_sms,
                                           cudaStream_t stream);
+extern "C" cudaError_t nrl_gemm_tc_fp8(const CUtensorMap* maps, const nrl::tc::TcParams* p, int cg, int bn, int swiglu, int num_sms,
+                                       cudaStream_t stream);
 // batched K-major x K-major GEMM, bf16 out; maps = {A, B, D} 3D (tma_host.h make_tma_3d), B box rows = bn / cg
 extern "C" cudaError_t nrl_gemm_tc_batched(const CUtensorMap* maps, const nrl::tc::TcParams* p, int cg, int bn, int num_sms,
                                            cudaStream_t stream);

@@ -8,9 +8,12 @@
 //                  so decode never allocates and the whole decode loop can live in one CUDA graph;
 //     on_demand  - pages are allocated at page boundaries during decode; when the pool runs dry the
 //                  youngest running group is preempted (pages freed, group re-queued for recompute).
+// NRL_RUNTIME_NO_PYBIND: the classes alone (csrc/runtime_asan_test.cpp builds them with -fsanitize=address,undefined)
+#ifndef NRL_RUNTIME_NO_PYBIND
 #include "runtime.h"
 
 #include <pybind11/stl.h>
+#endif
 
 #include <algorithm>
 #include <deque>
@@ -18,7 +21,9 @@
 #include <unordered_map>
 #include <vector>
 
+#ifndef NRL_RUNTIME_NO_PYBIND
 namespace py = pybind11;
+#endif
 
 namespace nrl {
 
@@ -257,6 +262,7 @@ class Scheduler {
   std::vector<int> running_;
 };
 
+#ifndef NRL_RUNTIME_NO_PYBIND
 void bind_runtime(py::module_& m) {
   py::class_<BlockManager>(m, "BlockManager")
       .def(py::init<int, int>(), py::arg("num_blocks"), py::arg("block_size"))
@@ -287,5 +293,6 @@ void bind_runtime(py::module_& m) {
       .def("running_groups", &Scheduler::running_groups)
       .def("prefill_slots", &Scheduler::prefill_slots);
 }
+#endif
 
 }  // namespace nrl

@@ -96,7 +96,7 @@ class NativeSampler:
             native._count(2)
             xq, xs = native.ext().quant_rows_e4m3(x)
             wq, ws = lw.q8[name]
-            return native.ext().gemm_fp8(xq, xs, wq, ws, bias, False)
+            return native.ext().gemm_tc_fp8(xq, xs, wq, ws, bias, False)          # kind::f8f6f4 on CTA pairs (gemm_tc.cu)
         return _gemm.gemm(x, getattr(lw, name), bias=bias, split_k=0)      # general tcgen05 GEMM (cta_group::2 where it pays)
 
     def quantize_arena(self):
@@ -195,9 +195,9 @@ class NativeSampler:
             hq, hs = native.ext().quant_rows_e4m3(h)
             if lw.wgu_i is not None:
                 wq, ws = lw.q8["wgu_i"]
-                return native.ext().gemm_fp8(hq, hs, wq, ws, None, True)
+                return native.ext().gemm_tc_fp8(hq, hs, wq, ws, None, True)
             wq, ws = lw.q8["wgu"]
-            return native.ext().swiglu(native.ext().gemm_fp8(hq, hs, wq, ws, None, False))
+            return native.ext().swiglu(native.ext().gemm_tc_fp8(hq, hs, wq, ws, None, False))
         if lw.wgu_i is not None:
             native._count()
             return native.ext().gemm_tc_swiglu(h, lw.wgu_i, None)

@@ -129,3 +129,29 @@ def test_batched_strided_heads(cg, bn):
         out = _ext().gemm_tc_batched(x.transpose(0, 1), pos, None, cg, bn)
         want = torch.bmm(x.float().transpose(0, 1), pos.float().transpose(1, 2))
         _check(out, want, k=dh)
+
+
+@pytest.mark.parametrize("cg,bn", [(1, 128), (1, 256), (2, 128), (2, 192), (2, 256), (0, 0)])
+def test_fp8_e4m3_gemm(cg, bn):
+    """kind::f8f6f4 GEMM with per-token x per-channel scales (the fp8 rollout path), plain and SwiGLU epilogues."""
+    ext = _ext()
+    torch.manual_seed(0)
+    for (M, N, K, sw) in ((300, 512, 256, False), (1024, 2048, 1536, False), (512, 1536, 8960, False), (256, 1024, 512, True), (1024, 17920, 1536, True)):
+        if sw and bn == 192:
+            continue
+        x = torch.randn(M, K, device="cuda").bfloat16()
+        w = (torch.randn(N, K, device="cuda") * 0.05).bfloat16()
+        xq, xs = ext.quant_rows_e4m3(x)
+        wq, ws = ext.quant_rows_e4m3(w)
+        xd = xq.view(torch.float8_e4m3fn).float() * xs[:, None]
+        wd = wq.view(torch.float8_e4m3fn).float() * ws[:, None]
+        bias = torch.randn(N, device="cuda").bfloat16() if not sw else None
+        out = ext.gemm_tc_fp8(xq, xs, wq, ws, bias, sw, cg, bn)
+        z = xd @ wd.t()
+        if sw:
+            F = N // 2
+            zz = z.view(M, F // 32, 2, 32)
+            want = (torch.nn.functional.silu(zz[:, :, 0]) * zz[:, :, 1]).reshape(M, F)
+        else:
+            want = z + bias.float()
+        _check(out, want, rel=1e-2, k=K)

@@ -59,3 +59,18 @@ def test_on_demand_preemption_and_recompute():
     assert s.num_waiting() == 1 and s.running_groups() == [g0]
     s.finish(s.group_seqs(g0))
     assert s.admit() == [g1] and s.admissions(g1) == 2
+
+
+def test_runtime_under_address_and_ub_sanitizers():
+    """the host runtime built with -fsanitize=address,undefined survives a randomized
+    admit / advance / finish / preempt workload with page accounting checked every step."""
+    import os
+    import shutil
+    import subprocess
+    if shutil.which("g++") is None:
+        import pytest
+        pytest.skip("no host compiler")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run(["bash", os.path.join(root, "bench", "asan_runtime.sh")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "all 257 pages returned" in r.stdout
