@@ -91,4 +91,42 @@ if which in ("all", "sample"):
     rid = torch.arange(1024, device=dev, dtype=torch.int32)
     for _ in range(3):
         native.sample(logits, 0.9, 0.95, 1, 0, rid, rid)
+if which in ("all", "deberta_tma"):
+    from nanorlhf_b200.models.deberta_v3 import build_bucket_lut
+    lens = [1660] * 8
+    cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), device=dev, dtype=torch.int32)
+    T = sum(lens)
+    q, k, v = (torch.randn(T, 16, 64, device=dev, dtype=torch.bfloat16) for _ in range(3))
+    ra, rb = (torch.randn(16, T, 512, device=dev, dtype=torch.bfloat16) for _ in range(2))
+    lut = build_bucket_lut(1660, 256, 512, 256, dev)
+    for _ in range(3):
+        native.ext().deberta_attn_fwd(q, k, v, cu, 1660, 1 / math.sqrt(192), ra, rb, lut)
+if which in ("all", "dlogits"):
+    h = torch.randn(8192, 1536, device=dev, dtype=torch.bfloat16)
+    w = (torch.randn(151936, 1536, device=dev) * 0.02).bfloat16()
+    t = torch.randint(0, 151936, (8192,), device=dev, dtype=torch.int32)
+    lse = torch.full((8192,), 12.0, device=dev)
+    g = torch.randn(8192, device=dev)
+    for _ in range(3):
+        native.ext().lmhead_dlogits(h, w, t, lse, g, 1 / 0.9)
+if which in ("all", "kar1"):
+    n = 540_672_000 // 8
+    G, P = torch.randn(n, device=dev).bfloat16(), torch.randn(n, device=dev).bfloat16()
+    m, v = torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+    mw = P.float()
+    for _ in range(3):                      # world = 1 instantiation of the P2P kernel: the HBM-side cost of K-AR
+        native.ext().allreduce_adam([G.data_ptr()], [P.data_ptr()], 0, 0, m, v, 0, n, 0, 6e-6, 0.9, 0.999, 1e-8, 0.0, 1, 1.0, False, 592, mw)
+if which in ("all", "rl"):
+    B, T = 256, 1500
+    nl, ol, adv, rl = (torch.randn(B, T, device=dev) for _ in range(4))
+    mk = torch.rand(B, T, device=dev) > 0.1
+    for _ in range(3):
+        native.ext().policy_loss(nl, ol, adv, mk, rl, 0.2, 0.01)
+        native.gae_scan(adv, nl, 1.0, 0.95)
+if which in ("all", "gemm_tc_fp8"):
+    x, w = torch.randn(1024, 1536, device=dev, dtype=torch.bfloat16), torch.randn(17920, 1536, device=dev, dtype=torch.bfloat16)
+    xq, xs = native.ext().quant_rows_e4m3(x)
+    wq, ws = native.ext().quant_rows_e4m3(w)
+    for _ in range(3):
+        native.ext().gemm_tc_fp8(xq, xs, wq, ws, None, True)
 torch.cuda.synchronize()
