@@ -252,13 +252,25 @@ class Qwen2PreTrained(nn.Module):
     @classmethod
     def from_config(cls, cfg: Qwen2Config, torch_dtype=torch.bfloat16, device="cpu", seed: Optional[int] = None):
         """Random-init (there is no network on the GPU box: SURVEY.md environment facts)."""
+        dev = torch.device(device)
+        # Billion-parameter models are initialised ON the GPU (seconds instead of ~half a minute of CPU normal_() per
+        # model -- start-up time counts against the benchmark driver's per-run limit); small models keep the CPU generator
+        # so CPU- and GPU-built test models with one seed stay identical.
+        big = dev.type == "cuda" and cfg.num_hidden_layers * cfg.hidden_size * cfg.intermediate_size > 5e7
         if seed is not None:
             gen_state = torch.random.get_rng_state()
+            cuda_state = torch.cuda.get_rng_state(dev) if big else None
             torch.manual_seed(seed)
-        model = cls(cfg)
+        if big:
+            with torch.device(dev):
+                model = cls(cfg)
+        else:
+            model = cls(cfg)
         _init_weights(model)
         if seed is not None:
             torch.random.set_rng_state(gen_state)
+            if big:
+                torch.cuda.set_rng_state(cuda_state, dev)
         model = model.to(device=device, dtype=torch_dtype)
         if hasattr(model, "tie_weights"):
             model.tie_weights()
