@@ -28,9 +28,57 @@ refresh_sampler_arena(local)
 want = [(lw.wqkv.clone(), lw.wo.clone(), lw.wgu.clone(), lw.wdown.clone()) for lw in local.layers]
 shared = NativeSampler(policy)
 sync = ShardedWeightSync(shared, comm)
+
+
+def mismatches():
+    """{(layer, matrix): number of differing elements} on this rank."""
+    bad = {}
+    for li, (lw, w) in enumerate(zip(shared.layers, want)):
+        for name, a, b in zip(("wqkv", "wo", "wgu", "wdown"), (lw.wqkv, lw.wo, lw.wgu, lw.wdown), w):
+            n = int((a != b).sum())
+            if n:
+                bad[f"L{li}.{name}"] = n
+    return bad
+
+
+# replicas must hold identical inputs: checksum of every parameter, compared across ranks
+chk = torch.stack([p.detach().float().sum() for p in policy.parameters()]).double().sum().reshape(1)
+allchk = comm.all_gather_cat(chk)
+inputs_identical = bool((allchk == allchk[0]).all())
 sync.refresh()
 torch.cuda.synchronize()
-ok = all(torch.equal(a, b) for lw, w in zip(shared.layers, want) for a, b in zip((lw.wqkv, lw.wo, lw.wgu, lw.wdown), w))
+bad_first = mismatches()
+import time as _time
+_time.sleep(0.2)
+torch.cuda.synchronize()
+bad_after_wait = mismatches()
+sync.refresh()
+torch.cuda.synchronize()
+bad_second = mismatches()
+# staleness probes: change the adapters, refresh, compare -- once as shipped, once draining the stream before the closing barrier,
+# once through plain peer stores (no multicast)
+probes = {}
+for tag in ("multicast", "multicast_drained", "peer_stores"):
+    with torch.no_grad():
+        for m in policy.modules():
+            if isinstance(m, LoraLinear):
+                m.lora_B.weight.mul_(1.25)
+    refresh_sampler_arena(local)
+    want = [(lw.wqkv.clone(), lw.wo.clone(), lw.wgu.clone(), lw.wdown.clone()) for lw in local.layers]
+    sync.drain_before_barrier = tag == "multicast_drained"
+    saved = sync.mc_base
+    if tag == "peer_stores":
+        sync.mc_base = 0
+    sync.refresh()
+    torch.cuda.synchronize()
+    probes[tag] = len(mismatches())
+    sync.mc_base = saved
+sync.drain_before_barrier = False
+ok = not bad_second and not bad_first and probes["multicast"] == 0
+diag = {"probes_mismatching_matrices": probes, "rank": comm.rank, "inputs_identical_across_ranks": inputs_identical, "first_refresh_mismatch": dict(list(bad_first.items())[:6]),
+        "n_first": len(bad_first), "n_after_200ms": len(bad_after_wait), "n_second_refresh": len(bad_second)}
+if bad_first or bad_second or not inputs_identical or any(probes.values()):
+    print("[wsync diag]", json.dumps(diag), file=sys.stderr, flush=True)
 
 
 def timed(fn, iters=5):
@@ -57,7 +105,7 @@ floor_ms = max(arena_gb * (W - 1) / W / 770.0, arena_gb / W / 6583.0) * 1e3
 verdict = torch.tensor([1 if ok else 0], device=dev)
 comm.all_reduce_(verdict, "min")
 ok = bool(verdict.item())
-res = {"world": W, "identical_to_local_merge": ok, "multicast": sync.stats["multicast"], "local_merge_ms": t_local,
+res = {"world": W, "identical_to_local_merge": ok, "inputs_identical_across_ranks": inputs_identical, "rank0_diag": diag, "multicast": sync.stats["multicast"], "local_merge_ms": t_local,
        "sharded_multicast_ms": t_sharded, "arena_gb": arena_gb, "nvlink_floor_ms": floor_ms,
        "frac_of_nvlink_roofline": floor_ms / t_sharded}
 if comm.is_main:

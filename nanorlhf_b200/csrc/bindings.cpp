@@ -933,6 +933,23 @@ void kv_cache_write_fp8(const torch::Tensor& k, const torch::Tensor& v, torch::T
                                kq.size(2), cur_stream()), "kv_cache_write_fp8");
 }
 
+// decode-step fusion: RoPE on the q and k heads of qkv [S, (Hq + 2 Hkv) * 128] in place + page write of (rotated k, v)
+void rope_kv_write(torch::Tensor qkv, const torch::Tensor& cos_t, const torch::Tensor& sin_t, torch::Tensor k_cache, torch::Tensor v_cache,
+                   const c10::optional<torch::Tensor>& k_scale, const c10::optional<torch::Tensor>& v_scale, const torch::Tensor& slot_mapping,
+                   int64_t Hq, int64_t Hkv) {
+  TORCH_CHECK(qkv.is_cuda() && qkv.scalar_type() == torch::kBFloat16 && qkv.dim() == 2 && qkv.stride(1) == 1 && qkv.size(1) == (Hq + 2 * Hkv) * 128);
+  TORCH_CHECK(cos_t.scalar_type() == torch::kFloat32 && cos_t.is_contiguous() && sin_t.is_contiguous() && cos_t.size(0) == qkv.size(0) && cos_t.size(1) == 64);
+  TORCH_CHECK(slot_mapping.scalar_type() == torch::kInt32 && slot_mapping.numel() == qkv.size(0) && slot_mapping.is_contiguous());
+  const bool kv8 = k_cache.scalar_type() == torch::kUInt8;
+  TORCH_CHECK(k_cache.is_contiguous() && v_cache.is_contiguous() && k_cache.size(1) == Hkv);
+  TORCH_CHECK(!kv8 || (k_scale.has_value() && v_scale.has_value()), "fp8 pages need their scale tensors");
+  c10::cuda::CUDAGuard guard(qkv.device());
+  check(nrl_rope_kv_write(qkv.data_ptr(), qkv.stride(0), cos_t.data_ptr<float>(), sin_t.data_ptr<float>(), k_cache.data_ptr(), v_cache.data_ptr(),
+                          kv8 ? k_scale->data_ptr<float>() : nullptr, kv8 ? v_scale->data_ptr<float>() : nullptr, slot_mapping.data_ptr<int>(),
+                          static_cast<int>(qkv.size(0)), static_cast<int>(Hq), static_cast<int>(Hkv), 128, 16, kv8 ? 1 : 0, cur_stream()),
+        "rope_kv_write");
+}
+
 torch::Tensor paged_decode_fp8(const torch::Tensor& q, const torch::Tensor& kq, const torch::Tensor& vq, const torch::Tensor& ks,
                                const torch::Tensor& vs, const torch::Tensor& block_tables, const torch::Tensor& context_lens,
                                double scale, int64_t splits) {
@@ -1011,6 +1028,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("kv_cache_write_fp8", &kv_cache_write_fp8, py::arg("k"), py::arg("v"), py::arg("kq"), py::arg("vq"), py::arg("ks"), py::arg("vs"),
         py::arg("slot_mapping"), py::arg("src_index") = py::none());
   m.def("paged_decode_fp8", &paged_decode_fp8);
+  m.def("rope_kv_write", &rope_kv_write);
   m.def("allreduce_adam", &allreduce_adam, py::arg("grad_ptrs"), py::arg("param_ptrs"), py::arg("grad_mc"), py::arg("param_mc"),
         py::arg("m"), py::arg("v"), py::arg("lo"), py::arg("n"), py::arg("rank"), py::arg("lr"), py::arg("beta1"), py::arg("beta2"),
         py::arg("eps"), py::arg("wd"), py::arg("step"), py::arg("grad_scale"), py::arg("use_multicast"), py::arg("max_blocks"),

@@ -21,7 +21,7 @@ OUT = os.path.join(PKG, "_C.so")
 OBJ = os.path.join(HERE, "build")
 CUDA_HOME = os.environ.get("CUDA_HOME", "/usr/local/cuda")
 
-CU_SOURCES = ["gemm_sm100.cu", "gemm_sm100_2cta.cu", "gemm_tc.cu", "elementwise.cu", "rl_kernels.cu", "sampling.cu", "attention_decode.cu", "attention_decode_fp8.cu", "attention_fwd_tc.cu", "attention_bwd_tc.cu",
+CU_SOURCES = ["gemm_sm100.cu", "gemm_sm100_2cta.cu", "gemm_tc.cu", "elementwise.cu", "rl_kernels.cu", "sampling.cu", "attention_decode.cu", "attention_decode_fp8.cu", "rope_kv.cu", "attention_fwd_tc.cu", "attention_bwd_tc.cu",
               "attention_varlen.cu", "comm.cu", "quant.cu"]
 CPP_SOURCES = ["bindings.cpp", "runtime.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--use_fast_math",

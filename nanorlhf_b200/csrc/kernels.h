@@ -92,3 +92,7 @@ cudaError_t nrl_paged_decode_fp8(const void* q, long q_stride_s, const void* kq,
                                  const int* block_tables, const int* context_lens, void* out, float* part_o, float* part_ml, int S,
                                  int Hq, int Hkv, int head_dim, int page, int max_blocks, int splits, float scale, cudaStream_t s);
 }
+
+extern "C" cudaError_t nrl_rope_kv_write(void* qkv, long stride_s, const float* cos_t, const float* sin_t, void* k_cache, void* v_cache,
+                                         float* k_scale, float* v_scale, const int* slot_mapping, int S, int Hq, int Hkv, int head_dim,
+                                         int page, int kv8, cudaStream_t s);

@@ -114,6 +114,7 @@ class ShardedWeightSync:
                 getattr(lw, name)  # must exist
                 setattr(lw, name, self.flat[off:off + a * b].view(a, b))
                 off += a * b
+        self.drain_before_barrier = False
         self.stats = {"refreshes": 0, "multicast": bool(self.mc_base)}
 
     def _mc_addr(self, view: torch.Tensor) -> int:
@@ -164,6 +165,10 @@ class ShardedWeightSync:
                 if b is not None:
                     lw.bqkv[sl].copy_(b)
             lw.ln1, lw.ln2 = layer.input_layernorm.weight, layer.post_attention_layernorm.weight
+        if self.drain_before_barrier:
+            # belt and braces for the multicast path: make sure this rank's kernels (and their posted NVLink / NVLS writes)
+            # have fully retired before it signals the closing barrier
+            torch.cuda.current_stream(s.device).synchronize()
         self.hdl.barrier(channel=1)                         # every rank's (multicast) stores have landed
         for lw in s.layers:
             interleave_gate_up(lw, F)

@@ -220,9 +220,11 @@ class NativeSampler:
         q = qkv[:, :Hq * D].view(S, Hq, D)
         k = qkv[:, Hq * D:(Hq + Hkv) * D].view(S, Hkv, D)
         v = qkv[:, (Hq + Hkv) * D:].view(S, Hkv, D)
-        native.ext().rope(q, cos, sin, 1.0, True)
-        native.ext().rope(k, cos, sin, 1.0, True)
-        self._kv_write(li, k, v, st["slot"], None)
+        # RoPE(q), RoPE(k) and the page write of (k, v) are one launch (csrc/rope_kv.cu)
+        native._count()
+        fp8 = self.kv_dtype == "fp8"
+        native.ext().rope_kv_write(qkv, cos, sin, self.k_cache[li], self.v_cache[li], self.k_scale[li] if fp8 else None,
+                                   self.v_scale[li] if fp8 else None, st["slot"], Hq, Hkv)
         if self.kv_dtype == "fp8":
             native._count()
             att = native.ext().paged_decode_fp8(q, self.k_cache[li], self.v_cache[li], self.k_scale[li], self.v_scale[li],

@@ -520,3 +520,38 @@ def test_adamw_flat_master_weights_lr_6e6():
     got = (master - w0.float()).abs().mean()
     assert abs(got - want) / want < 0.02
     assert torch.equal(p, master.bfloat16())
+
+
+@pytest.mark.parametrize("kv8", [False, True])
+def test_rope_kv_write_fused_matches_separate_kernels(kv8):
+    """Decode-step fusion (csrc/rope_kv.cu): RoPE(q) + RoPE(k) + page write in one launch == the three separate kernels."""
+    n = _native()
+    torch.manual_seed(0)
+    S, Hq, Hkv, D, nblk = 37, 12, 2, 128, 64
+    qkv = torch.randn(S, (Hq + 2 * Hkv) * D, device="cuda").bfloat16()
+    pos = torch.randint(0, 3000, (S,), device="cuda")
+    cos, sin = ref.rope_cos_sin(pos, D, 1e6)
+    slots = torch.randperm(nblk * 16, device="cuda")[:S].to(torch.int32)
+    # separate path
+    a = qkv.clone()
+    q = a[:, :Hq * D].view(S, Hq, D)
+    k = a[:, Hq * D:(Hq + Hkv) * D].view(S, Hkv, D)
+    v = a[:, (Hq + Hkv) * D:].view(S, Hkv, D)
+    n.ext().rope(q, cos, sin, 1.0, True)
+    n.ext().rope(k, cos, sin, 1.0, True)
+    if kv8:
+        kc1, vc1 = (torch.zeros(nblk, Hkv, 16, D, device="cuda", dtype=torch.uint8) for _ in range(2))
+        ks1, vs1 = (torch.ones(nblk, Hkv, 16, device="cuda") for _ in range(2))
+        n.ext().kv_cache_write_fp8(k, v, kc1, vc1, ks1, vs1, slots, None)
+    else:
+        kc1, vc1 = (torch.zeros(nblk, Hkv, 16, D, device="cuda", dtype=torch.bfloat16) for _ in range(2))
+        n.kv_cache_write(k, v, kc1, vc1, slots)
+    # fused path
+    b = qkv.clone()
+    kc2, vc2 = torch.zeros_like(kc1), torch.zeros_like(vc1)
+    ks2, vs2 = (torch.ones(nblk, Hkv, 16, device="cuda") for _ in range(2)) if kv8 else (None, None)
+    n.ext().rope_kv_write(b, cos, sin, kc2, vc2, ks2, vs2, slots, Hq, Hkv)
+    assert torch.equal(a, b)
+    assert torch.equal(kc1, kc2) and torch.equal(vc1, vc2)
+    if kv8:
+        assert torch.equal(ks1, ks2) and torch.equal(vs1, vs2)
