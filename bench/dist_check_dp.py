@@ -51,6 +51,7 @@ def micro(model, rows, scale):
 
 
 dp = build()
+comm.broadcast_module_(dp, 0)
 opt = FusedAdamW(build_param_groups(dp.named_parameters(), 0.0, LR), lr=LR, comm=comm, comm_mode="fused")
 opt.zero_grad()
 micro(dp, torch.arange(R, G, W, device=dev), 1.0)

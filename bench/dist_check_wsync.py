@@ -23,6 +23,7 @@ with torch.no_grad():
     for m in policy.modules():
         if isinstance(m, LoraLinear):
             m.lora_B.weight.copy_(torch.randn(m.lora_B.weight.shape, generator=g, device=dev, dtype=torch.float32).mul_(0.02))
+comm.broadcast_module_(policy, 0)          # replicas start identical (the trainer does the same for every model it holds)
 local = NativeSampler(policy)
 refresh_sampler_arena(local)
 want = [(lw.wqkv.clone(), lw.wo.clone(), lw.wgu.clone(), lw.wdown.clone()) for lw in local.layers]

@@ -101,6 +101,38 @@ class Comm:
             dist.broadcast(t, src=src)
         return t
 
+    def broadcast_module_(self, module, src: int = 0, only_frozen: bool = False) -> int:
+        """Make a module's parameters and buffers identical to rank ``src``'s (what DDP's constructor does for everything
+        it wraps).  Tensors are coalesced per dtype into flat staging buffers so a 1.5B model is a handful
+        of NCCL broadcasts.  ``only_frozen`` skips trainable parameters (the optimizer broadcasts its flat buffers itself).
+        Returns the number of bytes broadcast."""
+        if self.world_size == 1 or module is None:
+            return 0
+        seen, by_dtype = set(), {}
+        for t in list(module.parameters()) + list(module.buffers()):
+            if id(t) in seen or t.numel() == 0 or (only_frozen and getattr(t, "requires_grad", False)):
+                continue
+            seen.add(id(t))
+            by_dtype.setdefault((t.dtype, t.device), []).append(t)
+        total = 0
+        for (_dt, _dev), ts in by_dtype.items():
+            chunk, n = [], 0
+            for t in ts + [None]:
+                if t is not None:
+                    chunk.append(t)
+                    n += t.numel()
+                if chunk and (t is None or n >= (1 << 28)):          # <= ~0.5 GB (bf16) staging at a time
+                    flat = torch.cat([c.detach().reshape(-1) for c in chunk])
+                    dist.broadcast(flat, src=src)
+                    off = 0
+                    with torch.no_grad():
+                        for c in chunk:
+                            c.copy_(flat[off:off + c.numel()].view(c.shape))
+                            off += c.numel()
+                    total += flat.numel() * flat.element_size()
+                    chunk, n = [], 0
+        return total
+
     def reduce_scalars(self, values: Dict[str, float], op: str = "mean") -> Dict[str, float]:
         """Pack a dict of python floats into ONE vector and all-reduce it."""
         if self.world_size == 1:

@@ -26,6 +26,9 @@ class FusedAllReduceAdam:
         self.max_blocks = max_blocks
         self.use_multicast = os.environ.get("NANORLHF_NVLS", use_multicast)
         self.bytes_reduced = 0
+        # every cross-rank wait is bounded: a rank that died or diverged turns into a device-side trap (CUDA error -> non-zero
+        # exit -> restart from the last checkpoint) instead of an infinite spin that only the job scheduler can end
+        self.barrier_timeout_ms = int(float(os.environ.get("NANORLHF_BARRIER_TIMEOUT_S", "900")) * 1000)
         self.wait_events = []      # (start, end) around the opening barrier of every K-AR step: time spent waiting for the slowest rank
         native.load()
 
@@ -63,14 +66,14 @@ class FusedAllReduceAdam:
         use_mc = bool(mc_g and mc_p)
         w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         w0.record()
-        gh.barrier(channel=0)                      # every rank's backward has finished writing its gradients
+        gh.barrier(channel=0, timeout_ms=self.barrier_timeout_ms)                      # every rank's backward has finished writing its gradients
         w1.record()
         self.wait_events.append((w0, w1))
         native._count()
         native.ext().allreduce_adam(list(gh.buffer_ptrs), list(ph.buffer_ptrs), mc_g, mc_p, f.exp_avg, f.exp_avg_sq,
                                     lo, n, rank, hp["lr"], hp["beta1"], hp["beta2"], hp["eps"], hp["wd"], hp["step"],
                                     scale, use_mc, self.max_blocks, getattr(f, "master", None))
-        ph.barrier(channel=1)                      # updated parameters are visible on every rank
+        ph.barrier(channel=1, timeout_ms=self.barrier_timeout_ms)                      # updated parameters are visible on every rank
         self.bytes_reduced += f.padded * f.grad.element_size()
 
     def pop_wait_ms(self) -> float:
@@ -89,8 +92,8 @@ class FusedAllReduceAdam:
         per = (t.numel() // world) // 8 * 8
         lo = rank * per
         n = per if rank < world - 1 else t.numel() - lo
-        h.barrier(channel=0)
+        h.barrier(channel=0, timeout_ms=self.barrier_timeout_ms)
         native._count()
         native.ext().allreduce_sum(list(h.buffer_ptrs), lo, n, rank, scale, self.max_blocks)
-        h.barrier(channel=1)
+        h.barrier(channel=1, timeout_ms=self.barrier_timeout_ms)
         return t

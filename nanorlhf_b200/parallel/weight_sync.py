@@ -115,6 +115,8 @@ class ShardedWeightSync:
                 setattr(lw, name, self.flat[off:off + a * b].view(a, b))
                 off += a * b
         self.drain_before_barrier = False
+        import os
+        self.barrier_timeout_ms = int(float(os.environ.get("NANORLHF_BARRIER_TIMEOUT_S", "900")) * 1000)
         self.stats = {"refreshes": 0, "multicast": bool(self.mc_base)}
 
     def _mc_addr(self, view: torch.Tensor) -> int:
@@ -146,7 +148,7 @@ class ShardedWeightSync:
         cfg = s.cfg
         D = cfg.head_dim
         nq, nkv, F = cfg.num_attention_heads * D, cfg.num_key_value_heads * D, cfg.intermediate_size
-        self.hdl.barrier(channel=0)                         # nobody is still sampling from the old arena
+        self.hdl.barrier(channel=0, timeout_ms=self.barrier_timeout_ms)                         # nobody is still sampling from the old arena
         for li in range(cfg.num_hidden_layers):
             layer, lw = s.lm.model.layers[li], s.layers[li]
             at, mlp = layer.self_attn, layer.mlp
@@ -169,7 +171,7 @@ class ShardedWeightSync:
             # belt and braces for the multicast path: make sure this rank's kernels (and their posted NVLink / NVLS writes)
             # have fully retired before it signals the closing barrier
             torch.cuda.current_stream(s.device).synchronize()
-        self.hdl.barrier(channel=1)                         # every rank's (multicast) stores have landed
+        self.hdl.barrier(channel=1, timeout_ms=self.barrier_timeout_ms)                         # every rank's (multicast) stores have landed
         for lw in s.layers:
             interleave_gate_up(lw, F)
         self.stats["refreshes"] += 1

@@ -119,6 +119,13 @@ class RLTrainer:
             if self.model.value_model is not None:
                 self.model.value_model.gradient_checkpointing_enable(args.gradient_checkpointing_kwargs)
 
+        # Replicas must hold identical weights -- frozen ones included (base model under LoRA, reference policy, reward
+        # model): the reference gets this from DDP's constructor broadcast.  Seeds alone are not enough:
+        # device-side random init is not guaranteed to be bit-identical across processes.
+        if self.comm.world_size > 1:
+            for m in (policy, ref_policy, value_model if self.uses_value_model else None, getattr(reward_func, "rm", None)):
+                if isinstance(m, nn.Module):
+                    self.comm.broadcast_module_(m, 0)
         self.optimizer, self.lr_scheduler = optimizers
         if self.optimizer is None:
             self.optimizer = self.create_optimizer()
@@ -199,9 +206,9 @@ class RLTrainer:
         return {"responses": responses}
 
     def _weight_sync_kw(self) -> dict:
-        """``weight_sync="sharded"`` (default under fused DP on CUDA): the sampler arena refresh is K-BC across ranks."""
+        """``weight_sync="sharded"`` (fused DP on CUDA): the sampler arena refresh is K-BC across ranks."""
         a = self.args
-        if (self.comm.world_size > 1 and self.device.type == "cuda" and a.comm == "fused" and a.weight_sync != "local"
+        if (self.comm.world_size > 1 and self.device.type == "cuda" and a.comm == "fused" and a.weight_sync == "sharded"
                 and a.sampler != "torch" and hasattr(self.policy, "peft_config")):
             return {"weight_sync_comm": self.comm}
         return {}

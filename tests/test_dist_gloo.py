@@ -46,3 +46,33 @@ def test_two_rank_training_keeps_replicas_identical(algo):
     port = 29600 + (os.getpid() % 200) + (0 if algo == "grpo" else 1)
     with tempfile.TemporaryDirectory() as tmp:
         mp.spawn(_worker, args=(2, port, tmp, algo), nprocs=2, join=True)
+
+
+def _bcast_worker(rank, world, port, q):
+    import os
+    import torch
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    from nanorlhf_b200.parallel.comm import Comm
+    comm = Comm.from_env(torch.device("cpu"))
+    torch.manual_seed(100 + rank)                      # replicas deliberately start different
+    m = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.LayerNorm(16), torch.nn.Linear(16, 4)).to(torch.float32)
+    m[2].weight.requires_grad_(False)
+    m.register_buffer("step", torch.tensor([rank], dtype=torch.int64))
+    comm.broadcast_module_(m, 0)
+    sig = torch.cat([p.detach().reshape(-1) for p in m.parameters()] + [m.step.float()]).double().sum().item()
+    q.put((rank, sig))
+    comm.barrier()
+    comm.close()
+
+
+def test_broadcast_module_makes_replicas_identical():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_bcast_worker, args=(r, 2, 29611, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(60)
+    assert got[0] == got[1]
