@@ -340,7 +340,6 @@ class DebertaV3ForSequenceClassification(nn.Module):
         st = torch.random.get_rng_state()
         dev = torch.device(device)
         big = dev.type == "cuda" and cfg.num_hidden_layers * cfg.hidden_size * cfg.intermediate_size > 5e7   # see qwen2.from_config
-        cuda_state = torch.cuda.get_rng_state(dev) if big else None
         if seed is not None:
             torch.manual_seed(seed)
         if big:
@@ -354,8 +353,6 @@ class DebertaV3ForSequenceClassification(nn.Module):
                 if getattr(mod, "bias", None) is not None:
                     nn.init.zeros_(mod.bias)
         torch.random.set_rng_state(st)
-        if big:
-            torch.cuda.set_rng_state(cuda_state, dev)
         return m.to(device=device, dtype=torch_dtype)
 
     @classmethod

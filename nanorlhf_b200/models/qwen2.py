@@ -259,7 +259,8 @@ class Qwen2PreTrained(nn.Module):
         big = dev.type == "cuda" and cfg.num_hidden_layers * cfg.hidden_size * cfg.intermediate_size > 5e7
         if seed is not None:
             gen_state = torch.random.get_rng_state()
-            cuda_state = torch.cuda.get_rng_state(dev) if big else None
+            # torch.manual_seed also seeds every CUDA generator -- deliberately NOT undone: default CUDA generators start from a
+            # non-deterministic per-process seed, and modules created right after (LoRA adapters) must match across ranks
             torch.manual_seed(seed)
         if big:
             with torch.device(dev):
@@ -269,8 +270,6 @@ class Qwen2PreTrained(nn.Module):
         _init_weights(model)
         if seed is not None:
             torch.random.set_rng_state(gen_state)
-            if big:
-                torch.cuda.set_rng_state(cuda_state, dev)
         model = model.to(device=device, dtype=torch_dtype)
         if hasattr(model, "tie_weights"):
             model.tie_weights()
