@@ -184,7 +184,7 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": value / BASELINE_EPISODES_PER_S,
             "vs_baseline_note": "denominator = the reference README's ~1 episode/s on 1 x A100-40G with real weights (its only "
-                                "published throughput); not a same-box ratio -- see BASELINE.md section 3 for same-box anchors",
+                                "published throughput); not a same-box ratio -- see BASELINE.md section 2 for same-box anchors",
             "dtype": "bf16",
             "data": "synthetic hh-rlhf-shaped token prompts; random-init weights (no network)",
             "impl": "ours",

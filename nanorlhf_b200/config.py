@@ -126,9 +126,9 @@ class RLConfig:
 
     # ---- runtime (B200) --------------------------------------------------------------------
     comm: str = "fused"                         # fused (symmetric-memory kernels) | nccl
-    weight_sync: str = "local"                  # local (every rank merges its own arena, 13 ms) | sharded (K-BC: layer-sharded merge +
-                                                # multimem.st into every rank's arena: 7.4 ms and bit-identical at 2 GPUs; an 8-GPU
-                                                # run showed stale tiles after the closing barrier -- see DESIGN.md section 8 -- so opt-in)
+    weight_sync: str = "sharded"                # sharded (K-BC under fused DP: layer-sharded merge + multimem.st into every rank's arena,
+                                                # 7.4 ms at 2 GPUs / 5.8 ms at 8, bit-identical to the local merge) | local (every rank
+                                                # merges its own arena, 13.7 ms); single-GPU runs always merge locally
     train_cuda_graph: str = "auto"              # auto | on | off : replay the micro-step (fwd+loss+bwd) as a CUDA graph
     offload_policy: str = "resident"            # per-role residency: resident | host
     offload_ref: Optional[str] = None

@@ -216,6 +216,17 @@ def get_peft_model(model: nn.Module, config: LoraConfig) -> PeftModel:
     return PeftModel(model, config)
 
 
+def lora_group_forward(x, mods):
+    """``[m(x) for m in mods]`` for projections that share their input; when all of them are plain LoRA layers with the
+    same rank / scaling their rank-r projections run as one launch (ops.lora_linear_group)."""
+    if (len(mods) > 1 and all(isinstance(m, LoraLinear) for m in mods)
+            and all(isinstance(m.lora_dropout, nn.Identity) and not m.base_layer.weight.requires_grad for m in mods)
+            and len({(m.r, m.scaling) for m in mods}) == 1):
+        return ops.lora_linear_group(x, [(m.base_layer.weight, m.base_layer.bias, m.lora_A.weight, m.lora_B.weight) for m in mods],
+                                     mods[0].scaling)
+    return [m(x) for m in mods]
+
+
 def iter_lora_layers(model: nn.Module):
     for name, mod in model.named_modules():
         if isinstance(mod, LoraLinear):

@@ -125,9 +125,11 @@ class Qwen2Attention(nn.Module):
     def forward(self, x, cos, sin, cu_seqlens, max_seqlen):
         cfg = self.cfg
         T = x.shape[0]
-        q = self.q_proj(x).view(T, cfg.num_attention_heads, cfg.head_dim)
-        k = self.k_proj(x).view(T, cfg.num_key_value_heads, cfg.head_dim)
-        v = self.v_proj(x).view(T, cfg.num_key_value_heads, cfg.head_dim)
+        from .lora import lora_group_forward
+        q, k, v = lora_group_forward(x, [self.q_proj, self.k_proj, self.v_proj])        # one rank-r launch when all three carry LoRA
+        q = q.view(T, cfg.num_attention_heads, cfg.head_dim)
+        k = k.view(T, cfg.num_key_value_heads, cfg.head_dim)
+        v = v.view(T, cfg.num_key_value_heads, cfg.head_dim)
         q = ops.apply_rope(q, cos, sin)
         k = ops.apply_rope(k, cos, sin)
         o = ops.attention_varlen(q, k, v, cu_seqlens, max_seqlen, causal=True)
@@ -142,7 +144,9 @@ class Qwen2MLP(nn.Module):
         self.down_proj = Linear(cfg.intermediate_size, cfg.hidden_size, bias=False)
 
     def forward(self, x):
-        return self.down_proj(ops.swiglu_pair(self.gate_proj(x), self.up_proj(x)))
+        from .lora import lora_group_forward
+        gate, up = lora_group_forward(x, [self.gate_proj, self.up_proj])
+        return self.down_proj(ops.swiglu_pair(gate, up))
 
 
 class Qwen2DecoderLayer(nn.Module):

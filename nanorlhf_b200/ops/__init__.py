@@ -100,6 +100,17 @@ def lora_linear(x, weight, bias, lora_a, lora_b, scaling: float):
     return ref.lora_linear(x, weight, bias, lora_a, lora_b, scaling)
 
 
+def lora_linear_group(x, projs, scaling: float):
+    """LoRA projections that share their input (q/k/v, gate/up): ``projs`` = [(W, bias, A, B), ...] -> list of outputs.
+    One rank-r launch for all adapters on CUDA bf16 (ops/gemm.py); independent ``lora_linear`` calls elsewhere."""
+    if use_native(x):
+        _nat()
+        from . import gemm as _lin
+        if all(_lin.lora_supported(x, w, a, b) for w, _bias, a, b in projs) and len({a.shape[0] for _w, _b, a, _B in projs}) == 1:
+            return _lin.lora_linear_group(x, projs, scaling)
+    return [lora_linear(x, w, bias, a, b, scaling) for w, bias, a, b in projs]
+
+
 def attention_varlen(q, k, v, cu_seqlens, max_seqlen=None, causal=True, scale=None):
     if use_native(q):
         return _nat().attention_varlen(q, k, v, cu_seqlens, max_seqlen, causal, scale)

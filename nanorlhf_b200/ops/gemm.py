@@ -123,3 +123,54 @@ def lora_supported(x, w, a, b) -> bool:
 
 def lora_linear(x, w, bias, a, b, scaling: float):
     return _LoraLinearFn.apply(x, w, bias, a, b, float(scaling))
+
+
+class _LoraGroupFn(torch.autograd.Function):
+    """Several LoRA projections of ONE input (q / k / v, gate / up): the rank-r down-projections share a launch
+    (``t = s x [A_1; ...; A_n]^T``), each base GEMM takes its slice of ``t`` as dual-source-K operand, and in the backward the
+    adapter-input gradients ``dA_i`` come out of one GEMM over the concatenated ``t'`` while the whole LoRA term of ``dx`` rides
+    in the first dgrad GEMM (K2 = n r).  Compared with n independent ``_LoraLinearFn``: n - 1 fewer skinny launches per
+    direction, ``x`` is re-read once instead of n times."""
+
+    @staticmethod
+    def forward(ctx, x, scaling, n, *flat):
+        x2 = _rows(x)
+        ws, bs, As, Bs = flat[0::4], flat[1::4], flat[2::4], flat[3::4]
+        r = As[0].shape[0]
+        a_cat = torch.cat(As, 0)                                             # [n r, K]
+        t_cat = gemm(x2, a_cat, alpha=scaling)                               # [T, n r]
+        ys = [gemm(x2, ws[i], a2=t_cat[:, i * r:(i + 1) * r], b2=Bs[i], bias=bs[i]) for i in range(n)]
+        ctx.save_for_backward(x2, t_cat, a_cat, *ws, *Bs)
+        ctx.meta = (scaling, n, r, x.shape)
+        return tuple(y.view(*x.shape[:-1], y.shape[-1]) for y in ys)
+
+    @staticmethod
+    def backward(ctx, *gys):
+        s, n, r, xshape = ctx.meta
+        saved = ctx.saved_tensors
+        x2, t_cat, a_cat = saved[:3]
+        ws, Bs = saved[3:3 + n], saved[3 + n:3 + 2 * n]
+        gs = [_rows(g) for g in gys]
+        tp_cat = torch.empty(x2.shape[0], n * r, dtype=x2.dtype, device=x2.device)
+        for i in range(n):
+            gemm(gs[i], Bs[i], b_mn=True, alpha=s, out=tp_cat[:, i * r:(i + 1) * r])       # t'_i = s dy_i B_i
+        gx = None
+        if ctx.needs_input_grad[0]:
+            gx = gemm(gs[0], ws[0], b_mn=True, a2=tp_cat, b2=a_cat)                          # dy_0 W_0 + [t'_1 .. t'_n] [A_1; ..; A_n]
+            for i in range(1, n):
+                gx = gx + gemm(gs[i], ws[i], b_mn=True)
+            gx = gx.view(xshape)
+        ga_cat = gemm(tp_cat, x2, a_mn=True, b_mn=True)                                       # [n r, K]
+        grads = [gx, None, None]
+        for i in range(n):
+            gb = gemm(gs[i], t_cat[:, i * r:(i + 1) * r], a_mn=True, b_mn=True)             # [N_i, r]
+            grads += [None, None, ga_cat[i * r:(i + 1) * r], gb]
+        return tuple(grads)
+
+
+def lora_linear_group(x, projs, scaling: float):
+    """``projs``: [(W, bias | None, A, B), ...] sharing the input ``x`` -> list of outputs."""
+    flat = []
+    for w, bias, a, b in projs:
+        flat += [w, bias, a, b]
+    return list(_LoraGroupFn.apply(x, float(scaling), len(projs), *flat))

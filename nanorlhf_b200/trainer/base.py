@@ -206,7 +206,7 @@ class RLTrainer:
         return {"responses": responses}
 
     def _weight_sync_kw(self) -> dict:
-        """``weight_sync="sharded"`` (fused DP on CUDA): the sampler arena refresh is K-BC across ranks."""
+        """``weight_sync="sharded"`` (the default; needs fused DP on CUDA): the sampler arena refresh is K-BC across ranks."""
         a = self.args
         if (self.comm.world_size > 1 and self.device.type == "cuda" and a.comm == "fused" and a.weight_sync == "sharded"
                 and a.sampler != "torch" and hasattr(self.policy, "peft_config")):

@@ -23,10 +23,10 @@ def test_fused_allreduce_adam_matches_nccl():
 
 
 def test_sharded_multicast_weight_sync_matches_local_merge():
-    """K-BC: layer-sharded LoRA merge with multimem.st into every rank's sampler arena == the local merge, bit for bit.
-    Validated (and run) on 2 ranks; the 8-rank run of round 2 showed stale tiles after the closing barrier (DESIGN.md
-    section 8), which is why ``weight_sync`` defaults to the local merge."""
-    n = 2
+    """K-BC: layer-sharded LoRA merge with multimem.st into every rank's sampler arena == the local merge, bit for bit
+    (the check script broadcasts rank 0's adapters first, as the trainers do at start-up)."""
+    n = min(torch.cuda.device_count(), 8)
+    n = 1 << (n.bit_length() - 1)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
                         "--master-addr", "127.0.0.1", "--master-port", "29519", os.path.join(ROOT, "bench", "dist_check_wsync.py")],
                        capture_output=True, text=True, timeout=600)
