@@ -169,12 +169,14 @@ torch::Tensor gemm_tc(const torch::Tensor& a, const torch::Tensor& b, bool a_mn,
   }
   if (M == 0 || N == 0) return out;
   // ---- split-K: few output tiles, long contraction (rank-r projections, LoRA weight gradients) ----
-  if (cg_req <= 0 && bn_req <= 0 && K2 == 0 && !f32 && !bias.has_value() && act == 0 && (a_mn == b_mn || !a_mn) && splitk_req != 0) {
+  const bool bias_ok = !bias.has_value() || ((reinterpret_cast<uintptr_t>(bias->data_ptr()) & 15) == 0 && bias->is_contiguous());
+  if (cg_req <= 0 && bn_req <= 0 && K2 == 0 && !f32 && bias_ok && act == 0 && (a_mn == b_mn || !a_mn) && splitk_req != 0) {
     const int bn = N <= 64 ? 64 : 128;
     const int64_t tiles = ((M + 127) / 128) * ((N + bn - 1) / bn), num_kb = (K + 63) / 64;
     const int sms = num_sms();
     int64_t splits = splitk_req > 0 ? splitk_req : std::min<int64_t>(std::min<int64_t>(sms / std::max<int64_t>(tiles, 1), num_kb / 4), 16);
-    if (splitk_req > 0 || (tiles * 2 <= sms && N <= 128 && splits >= 2)) {
+    // (any N: the adapter-input gradient dA = t'^T x is [r, K_in] -- 12 or 24 tiles of a 6.6 k-long contraction)
+    if (splitk_req > 0 || (tiles * 2 <= sms && splits >= 2)) {
       splits = std::max<int64_t>(1, std::min<int64_t>(splits, num_kb));
       const int64_t per = (num_kb + splits - 1) / splits;
       splits = (num_kb + per - 1) / per;                                 // no empty k-range
@@ -193,6 +195,10 @@ torch::Tensor gemm_tc(const torch::Tensor& a, const torch::Tensor& b, bool a_mn,
       nrl::tc::TcParams ps{};
       ps.M = static_cast<int>(M); ps.N = static_cast<int>(N); ps.K = static_cast<int>(K); ps.K2 = 0;
       ps.alpha = static_cast<float>(alpha);
+      if (bias.has_value()) {
+        TORCH_CHECK(bias->is_cuda() && bias->scalar_type() == torch::kBFloat16 && bias->numel() == N, "gemm_tc: bias must be bf16 [N]");
+        ps.bias = reinterpret_cast<const __nv_bfloat16*>(bias->data_ptr());
+      }
       ps.splits = static_cast<int>(splits);
       ps.ws = ws.data_ptr<float>();
       ps.counters = counters.data_ptr<int>();
@@ -657,7 +663,7 @@ void adamw_flat(torch::Tensor param, const torch::Tensor& grad, torch::Tensor m,
 // ---- sampler kernels ------------------------------------------------------------------------------
 torch::Tensor sample(const torch::Tensor& logits, double temperature, double top_p, int64_t seed, int64_t step,
                      const c10::optional<torch::Tensor>& row_ids, const c10::optional<torch::Tensor>& row_steps,
-                     c10::optional<torch::Tensor> out_opt) {
+                     c10::optional<torch::Tensor> out_opt, int64_t impl) {
   TORCH_CHECK(logits.is_cuda() && logits.dim() == 2 && logits.stride(1) == 1);
   const bool bf16 = logits.scalar_type() == torch::kBFloat16;
   TORCH_CHECK(bf16 || logits.scalar_type() == torch::kFloat32);
@@ -670,7 +676,7 @@ torch::Tensor sample(const torch::Tensor& logits, double temperature, double top
   if (row_steps.has_value()) rst = row_steps->data_ptr<int>();
   check(nrl_sample(logits.data_ptr(), bf16 ? 1 : 0, logits.stride(0), logits.size(0), logits.size(1),
                    static_cast<float>(temperature), static_cast<float>(top_p), static_cast<unsigned long long>(seed),
-                   static_cast<unsigned long long>(step), rid, rst, out.data_ptr<int>(), cur_stream()), "sample");
+                   static_cast<unsigned long long>(step), rid, rst, out.data_ptr<int>(), static_cast<int>(impl), cur_stream()), "sample");
   return out;
 }
 
@@ -1012,7 +1018,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("adamw_flat", &adamw_flat, py::arg("param"), py::arg("grad"), py::arg("m"), py::arg("v"), py::arg("lr"), py::arg("beta1"),
         py::arg("beta2"), py::arg("eps"), py::arg("wd"), py::arg("step"), py::arg("grad_scale") = 1.0, py::arg("master") = py::none());
   m.def("sample", &sample, py::arg("logits"), py::arg("temperature"), py::arg("top_p"), py::arg("seed"), py::arg("step"),
-        py::arg("row_ids") = py::none(), py::arg("row_steps") = py::none(), py::arg("out") = py::none());
+        py::arg("row_ids") = py::none(), py::arg("row_steps") = py::none(), py::arg("out") = py::none(),
+        py::arg("impl") = 0);           // 0 = automatic, 1 = streaming kernel, 2 = shared-memory-resident cluster kernel
   m.def("kv_cache_write", &kv_cache_write, py::arg("k"), py::arg("v"), py::arg("k_cache"), py::arg("v_cache"),
         py::arg("slot_mapping"), py::arg("src_index") = py::none());
   m.def("paged_decode", &paged_decode, py::arg("q"), py::arg("k_cache"), py::arg("v_cache"), py::arg("block_tables"),

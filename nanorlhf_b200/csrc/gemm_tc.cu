@@ -381,8 +381,20 @@ NRL_DEVICE void gemm_tc_body(const CUtensorMap& tmA, const CUtensorMap& tmB, con
               const float4 y = __ldcg(reinterpret_cast<const float4*>(base + sp * split_stride + j + 4));
               s8[0] += x.x; s8[1] += x.y; s8[2] += x.z; s8[3] += x.w; s8[4] += y.x; s8[5] += y.y; s8[6] += y.z; s8[7] += y.w;
             }
-            *reinterpret_cast<uint4*>(orow + j) = make_uint4(pack_bf16x2(s8[0] * p.alpha, s8[1] * p.alpha), pack_bf16x2(s8[2] * p.alpha, s8[3] * p.alpha),
-                                                             pack_bf16x2(s8[4] * p.alpha, s8[5] * p.alpha), pack_bf16x2(s8[6] * p.alpha, s8[7] * p.alpha));
+#pragma unroll
+            for (int e = 0; e < 8; ++e) s8[e] *= p.alpha;
+            if (p.bias != nullptr) {
+              const uint4 bv = *reinterpret_cast<const uint4*>(p.bias + c.n_blk * BN + j);      // N % 8 == 0, bias 16-byte aligned
+              const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 bf = unpack_bf16x2(bw[e]);
+                s8[2 * e] += bf.x;
+                s8[2 * e + 1] += bf.y;
+              }
+            }
+            *reinterpret_cast<uint4*>(orow + j) = make_uint4(pack_bf16x2(s8[0], s8[1]), pack_bf16x2(s8[2], s8[3]),
+                                                             pack_bf16x2(s8[4], s8[5]), pack_bf16x2(s8[6], s8[7]));
           }
         }
         named_barrier_sync(1, kEpiThreads);                // s_last is rewritten by the next work item

@@ -38,7 +38,7 @@ cudaError_t nrl_adamw_flat(void* param, const void* grad, void* m, void* v, floa
 
 cudaError_t nrl_sample(const void* logits, int is_bf16, long row_stride, int rows, int V, float temperature,
                        float top_p, unsigned long long seed, unsigned long long step, const int* row_ids,
-                       const int* row_steps, int* out_tokens, cudaStream_t s);
+                       const int* row_steps, int* out_tokens, int impl, cudaStream_t s);
 }
 
 extern "C" {

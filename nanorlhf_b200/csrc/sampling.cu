@@ -6,9 +6,20 @@
 //   3. 64-slice histogram inside that octave                              -> cut-off resolved to 2^(1/64) = 1.1 %
 //   4. kept mass per thread; draw u ~ Philox(seed, row, step) in (0, kept mass] and walk the kept tokens
 // Histograms are lane-private shared-memory columns ([bin][lane]: bank == lane), so there are no atomics.
+//
+// Two kernels run that algorithm:
+//   sample_top_p_smem_kernel   bf16 rows up to 4 x 80 k tokens: a thread-block CLUSTER of C CTAs owns a row, each CTA pulls its
+//                              1/C slice into shared memory ONCE with bulk async copies (TMA, mbarrier completion) and all passes
+//                              run out of shared memory; the C partial results (max, histograms, kept mass) are exchanged through
+//                              distributed shared memory (st.shared::cluster + barrier.cluster).  HBM sees every logit once.
+//   sample_top_p_kernel        the streaming fallback (fp32 logits, rows that are not 16-byte sliceable, larger vocabularies):
+//                              one CTA per row, every pass re-reads the row through L2.
 // Reference: vLLM SamplingParams(temperature, top_p=0.95, seed=...) in vllm_generate
 // (/root/reference/GRPO/grpo_trainer.py:127) and the T=0 greedy pass of ReMax (remax_trainer.py:167).
 #include <curand_kernel.h>
+
+#include <cstdlib>
+#include <string>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -251,6 +262,235 @@ __global__ void __launch_bounds__(kSampThreads) sample_top_p_kernel(const T* __r
   }
 }
 
+
+// ---- shared-memory-resident variant: cluster of C CTAs per row --------------------------------------------------------------
+NRL_DEVICE uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+NRL_DEVICE uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+NRL_DEVICE void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// the address of `p` (a shared-memory object of this CTA) in the shared memory of CTA `rank` of the cluster
+NRL_DEVICE uint32_t map_to_rank(const void* p, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+  return r;
+}
+NRL_DEVICE void st_cluster_f32(uint32_t addr, float v) { asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+NRL_DEVICE void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+constexpr int kMaxCluster = 4;
+constexpr int kSliceBytesMax = 156 * 1024;                        // + 64 KB of histograms + ~6 KB static <= 227 KB per CTA
+constexpr int kHistBytes = (kSampThreads / 32) * 64 * 32 * 4;
+
+// every CTA of the cluster publishes `n` floats (n <= 64) into slot [my rank] of `dst` in every CTA; after the cluster barrier all
+// CTAs hold all contributions and reduce them in rank order (identical result everywhere).  Each exchange has its own slots: a
+// CTA can run at most one cluster barrier ahead of its peers, so a slot is never rewritten while a peer still reads it.
+NRL_DEVICE void cluster_publish(float (*dst)[64], const float* src, int n, uint32_t my_rank, uint32_t nrank) {
+#pragma unroll 1
+  for (int i = threadIdx.x; i < n * static_cast<int>(nrank); i += kSampThreads) {
+    const uint32_t peer = i / n;
+    const int k = i % n;
+    st_cluster_f32(map_to_rank(&dst[my_rank][k], peer), src[k]);
+  }
+  cluster_sync_all();
+}
+
+__global__ void __launch_bounds__(kSampThreads, 1) sample_top_p_smem_kernel(const __nv_bfloat16* __restrict__ logits, long row_stride,
+                                                                            int V, int slice, float inv_temp, float top_p,
+                                                                            unsigned long long seed, unsigned long long step,
+                                                                            const int* __restrict__ row_ids,
+                                                                            const int* __restrict__ row_steps,
+                                                                            int* __restrict__ out_tokens) {
+  extern __shared__ __align__(128) unsigned char s_dyn[];
+  float* s_hist = reinterpret_cast<float*>(s_dyn);                                   // [warps][64][32]
+  const __nv_bfloat16* zs = reinterpret_cast<const __nv_bfloat16*>(s_dyn + kHistBytes);   // this CTA's slice of the row
+  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ float red[32];
+  __shared__ float s_acc[64];
+  __shared__ float s_x[4][kMaxCluster][64];                // one set of exchange slots per exchange, written by the peers
+  __shared__ float chunk_sum[kSampThreads];
+  __shared__ float s_resid;
+  __shared__ int s_owner;
+  const uint32_t crank = cluster_ctarank(), csize = cluster_nctarank();
+  const int row = blockIdx.x / static_cast<int>(csize);
+  const int tid = threadIdx.x;
+  const int e0 = static_cast<int>(crank) * slice;                                     // first token of this CTA's slice
+  const int Vl = max(0, min(slice, V - e0));                                          // tokens in the slice (multiple of 8)
+  constexpr int VN = 8;
+  const int nvec = Vl / VN;
+  const float sc = inv_temp * 1.4426950408889634f;
+  float* my_hist = s_hist + (tid >> 5) * 64 * 32 + (tid & 31);
+
+  // ---- the only global read of the row: 1/C of it, as a few bulk async copies ----
+  if (tid == 0) {
+    mbar_init(&s_bar, 1);
+    fence_mbar_init();
+    const uint32_t bytes = static_cast<uint32_t>(Vl) * 2u;
+    if (bytes > 0) {
+      mbar_arrive_expect_tx(&s_bar, bytes);
+      const unsigned char* src = reinterpret_cast<const unsigned char*>(logits + static_cast<long>(row) * row_stride + e0);
+      for (uint32_t off = 0; off < bytes; off += 32768u)
+        bulk_load_1d(s_dyn + kHistBytes + off, src + off, min(32768u, bytes - off), &s_bar);
+    } else {
+      mbar_arrive(&s_bar);
+    }
+  }
+  hist_clear(s_hist);                                     // overlaps the copy; ends with __syncthreads (barrier init visible)
+  mbar_wait(&s_bar, 0);
+
+  // ---- pass 1: row maximum ----
+  float mx = -INFINITY;
+  for_each_elem(zs, nvec, Vl, [&](int, float x) { mx = fmaxf(mx, x * sc); });
+  mx = block_reduce_max(mx, red);
+  if (tid == 0) s_acc[0] = mx;
+  __syncthreads();
+  cluster_publish(s_x[0], s_acc, 1, crank, csize);
+  mx = s_x[0][0][0];
+  for (uint32_t r = 1; r < csize; ++r) mx = fmaxf(mx, s_x[0][r][0]);
+
+  float thresh = INFINITY;
+  if (top_p < 1.f) {
+    // ---- pass 2: one-octave mass histogram ----
+    for_each_elem(zs, nvec, Vl, [&](int, float x) {
+      const float d = mx - x * sc;
+      const int b = min(63, static_cast<int>(d));
+      my_hist[b * 32] += exp2f(-d);
+    });
+    hist_reduce(s_hist, s_acc);
+    cluster_publish(s_x[1], s_acc, 64, crank, csize);
+    float total = 0.f;
+    for (int k = 0; k < 64; ++k) {
+      float t = 0.f;
+      for (uint32_t r = 0; r < csize; ++r) t += s_x[1][r][k];
+      total += t;
+    }
+    const float target = top_p * total;
+    int B = 63;
+    float before = 0.f, cum = 0.f;
+    for (int k = 0; k < 64; ++k) {
+      float t = 0.f;
+      for (uint32_t r = 0; r < csize; ++r) t += s_x[1][r][k];
+      if (cum + t >= target) { B = k; before = cum; break; }
+      cum += t;
+    }
+    // ---- pass 3: 1/64-octave histogram inside octave B ----
+    hist_clear(s_hist);
+    for_each_elem(zs, nvec, Vl, [&](int, float x) {
+      const float d = mx - x * sc;
+      const int b = min(63, static_cast<int>(d));
+      if (b == B) {
+        const int f = min(63, static_cast<int>((d - static_cast<float>(B)) * 64.f));
+        my_hist[f * 32] += exp2f(-d);
+      }
+    });
+    hist_reduce(s_hist, s_acc);
+    cluster_publish(s_x[2], s_acc, 64, crank, csize);
+    int Fc = 63;
+    cum = before;
+    for (int k = 0; k < 64; ++k) {
+      float t = 0.f;
+      for (uint32_t r = 0; r < csize; ++r) t += s_x[2][r][k];
+      cum += t;
+      if (cum >= target) { Fc = k; break; }
+    }
+    thresh = (B >= 63 && Fc >= 63) ? INFINITY : static_cast<float>(B) + static_cast<float>(Fc + 1) * (1.f / 64.f);
+  }
+
+  // ---- pass 4: kept mass per thread, per CTA; the CTA whose cumulative range holds the draw walks its slice ----
+  float mine = 0.f;
+  for_each_elem(zs, nvec, Vl, [&](int, float x) {
+    const float d = mx - x * sc;
+    if (d < thresh) mine += exp2f(-d);
+  });
+  chunk_sum[tid] = mine;
+  const float cta_mass = block_reduce_sum(mine, red);       // (its barriers also publish chunk_sum)
+  if (tid == 0) s_acc[0] = cta_mass;
+  __syncthreads();
+  cluster_publish(s_x[3], s_acc, 1, crank, csize);
+  float total = 0.f, excl_cta = 0.f;
+  int last_with_mass = 0;
+  for (uint32_t r = 0; r < csize; ++r) {
+    if (r == crank) excl_cta = total;
+    total += s_x[3][r][0];
+    if (s_x[3][r][0] > 0.f) last_with_mass = static_cast<int>(r);
+  }
+  float u;
+  {
+    curandStatePhilox4_32_10_t st;                         // every thread of every CTA derives the same draw
+    curand_init(seed, static_cast<unsigned long long>(row_ids ? row_ids[row] : row),
+                step + (row_steps ? static_cast<unsigned long long>(row_steps[row]) : 0ull), &st);
+    u = curand_uniform(&st) * total;                       // (0, total]
+  }
+  int owner_cta = last_with_mass;
+  {
+    float acc = 0.f;
+    for (uint32_t r = 0; r < csize; ++r) {
+      if (s_x[3][r][0] > 0.f && acc + s_x[3][r][0] >= u) { owner_cta = static_cast<int>(r); break; }
+      acc += s_x[3][r][0];
+    }
+  }
+  if (owner_cta != static_cast<int>(crank)) return;        // no remote access follows the last cluster barrier
+  u = fminf(fmaxf(u - excl_cta, 0.f), cta_mass);           // the draw, local to this CTA's kept mass
+  if (tid < 32) {
+    float local[kPerLane];
+    float tsum = 0.f;
+#pragma unroll
+    for (int i = 0; i < kPerLane; ++i) { local[i] = chunk_sum[tid * kPerLane + i]; tsum += local[i]; }
+    float incl = tsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      float y = __shfl_up_sync(0xffffffffu, incl, o);
+      if (tid >= o) incl += y;
+    }
+    const float excl = incl - tsum;
+    const unsigned has = __ballot_sync(0xffffffffu, tsum > 0.f);
+    const unsigned ball = __ballot_sync(0xffffffffu, (incl >= u) && (tsum > 0.f));
+    const int wl = ball ? (__ffs(ball) - 1) : (has ? 31 - __clz(has) : 31);      // numerical slack: the last lane with mass
+    if (tid == wl) {
+      float acc2 = excl;
+      int owner = tid * kPerLane + kPerLane - 1;
+      float resid = 0.f;
+      bool hit = false;
+      for (int i = 0; i < kPerLane; ++i) {
+        if (!hit && local[i] > 0.f && acc2 + local[i] >= u) { owner = tid * kPerLane + i; resid = u - acc2; hit = true; }
+        if (!hit) acc2 += local[i];
+      }
+      if (!hit) {   // numerical slack: the last thread with mass takes it
+        for (int i = kPerLane - 1; i >= 0; --i) if (local[i] > 0.f) { owner = tid * kPerLane + i; resid = local[i]; break; }
+      }
+      s_owner = owner;
+      s_resid = resid;
+    }
+  }
+  __syncthreads();
+  if (tid == s_owner) {
+    const float resid = s_resid;
+    float acc2 = 0.f;
+    int tok = -1, last_kept = -1;
+    for (int v = tid; v < nvec && tok < 0; v += kSampThreads) {
+      float x[VN];
+      RowVec<__nv_bfloat16>::load(zs, v, x);
+#pragma unroll
+      for (int j = 0; j < VN; ++j)
+        if (tok < 0) {
+          const float d = mx - x[j] * sc;
+          if (d < thresh) {
+            last_kept = v * VN + j;
+            acc2 += exp2f(-d);
+            if (acc2 >= resid) tok = v * VN + j;
+          }
+        }
+    }
+    if (tok < 0) tok = last_kept >= 0 ? last_kept : 0;
+    out_tokens[row] = e0 + tok;
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kSampThreads) argmax_kernel(const T* __restrict__ logits, long row_stride, int V,
                                                               int* __restrict__ out_tokens) {
@@ -299,7 +539,7 @@ using namespace nrl;
 
 extern "C" cudaError_t nrl_sample(const void* logits, int is_bf16, long row_stride, int rows, int V, float temperature,
                                   float top_p, unsigned long long seed, unsigned long long step, const int* row_ids,
-                                  const int* row_steps, int* out_tokens, cudaStream_t s) {
+                                  const int* row_steps, int* out_tokens, int impl_req, cudaStream_t s) {
   if (rows == 0) return cudaSuccess;
   if (temperature == 0.f) {
     if (is_bf16)
@@ -315,6 +555,37 @@ extern "C" cudaError_t nrl_sample(const void* logits, int is_bf16, long row_stri
       cudaFuncSetAttribute(sample_top_p_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, hist_bytes);
       cudaFuncSetAttribute(sample_top_p_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, hist_bytes);
       configured = true;
+    }
+    // bf16 rows that slice into 16-byte aligned pieces of <= 160 KB: the shared-memory-resident cluster kernel
+    // impl_req: 0 = automatic (NANORLHF_SAMPLER_KERNEL=stream forces the fallback), 1 = streaming kernel, 2 = cluster kernel or error
+    static const int env_impl = [] { const char* e = std::getenv("NANORLHF_SAMPLER_KERNEL"); return e && std::string(e) == "stream" ? 1 : 0; }();
+    const int impl = impl_req != 0 ? impl_req : env_impl;
+    int csize = 1;
+    while (csize < kMaxCluster && (static_cast<long>(V) * 2 + csize - 1) / csize > kSliceBytesMax) csize *= 2;
+    const int slice = ((V + csize - 1) / csize + 7) / 8 * 8;
+    const bool smem_ok = is_bf16 && V % 8 == 0 && row_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0 &&
+                         static_cast<long>(slice) * 2 <= kSliceBytesMax;
+    if (impl == 2 && !smem_ok) return cudaErrorInvalidValue;
+    if (smem_ok && impl != 1) {
+      const int smem = kHistBytes + slice * 2;
+      static int configured_smem = 0;
+      if (smem > configured_smem) {
+        cudaError_t e = cudaFuncSetAttribute(sample_top_p_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHistBytes + kSliceBytesMax);
+        if (e != cudaSuccess) return e;
+        configured_smem = kHistBytes + kSliceBytesMax;
+      }
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(static_cast<unsigned>(rows) * csize, 1, 1);
+      cfg.blockDim = dim3(kSampThreads, 1, 1);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = s;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      return cudaLaunchKernelEx(&cfg, sample_top_p_smem_kernel, static_cast<const __nv_bfloat16*>(logits), row_stride, V, slice, inv_t,
+                                top_p, seed, step, row_ids, row_steps, out_tokens);
     }
     if (is_bf16)
       sample_top_p_kernel<__nv_bfloat16><<<rows, kSampThreads, hist_bytes, s>>>(static_cast<const __nv_bfloat16*>(logits), row_stride, V,

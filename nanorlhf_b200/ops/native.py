@@ -297,9 +297,9 @@ def adamw_flat(param, grad, m, v, lr, beta1, beta2, eps, wd, step, scale=1.0, ma
 # --------------------------------------------------------------------------------------------
 # sampler kernels
 # --------------------------------------------------------------------------------------------
-def sample(logits, temperature, top_p, seed, step, row_ids=None, row_steps=None, out=None):
+def sample(logits, temperature, top_p, seed, step, row_ids=None, row_steps=None, out=None, impl=0):
     _count()
-    return ext().sample(logits, float(temperature), float(top_p), int(seed), int(step), row_ids, row_steps, out)
+    return ext().sample(logits, float(temperature), float(top_p), int(seed), int(step), row_ids, row_steps, out, int(impl))
 
 
 def kv_cache_write(k, v, k_cache, v_cache, slot_mapping, src_index=None):

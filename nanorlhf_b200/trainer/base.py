@@ -476,7 +476,7 @@ class RLTrainer:
         """CUDA-graph replay of the micro-step (trainer/graphed.py) when the step is graph-safe."""
         a = self.args
         mode = getattr(a, "train_cuda_graph", "auto")
-        ok = (self.device.type == "cuda" and mode != "off" and not self.uses_value_model and a.lora_dropout == 0.0
+        ok = (self.device.type == "cuda" and mode != "off" and a.lora_dropout == 0.0
               and ops.use_native(torch.empty(0, device=self.device)))
         if mode == "auto":
             ok = ok and not a.gradient_checkpointing           # torch.utils.checkpoint is not captured

@@ -53,10 +53,16 @@ class GraphedMicroStep:
     # ---- the device-only micro-step ---------------------------------------------------------------
     def _body(self, plan, mb, B, T_r, L, accum):
         t, a = self.t, self.t.args
-        out_lp, out_ent, _ = planned_response_logprobs(t.policy, plan, B, T_r, a.temperature, True,
-                                                       max_seqlen=L)
+        out_lp, out_ent, hidden = planned_response_logprobs(t.policy, plan, B, T_r, a.temperature, True,
+                                                            max_seqlen=L)
         mb = dict(mb)
         mb["new_logprobs"] = torch.masked_fill(out_lp, mb["padding_mask"], INVALID_LOGPROB)
+        if t.uses_value_model:                               # PPO: the critic's forward / backward rides in the same graph
+            vm = t.model.value_model
+            vh = hidden if vm is t.policy else vm.hidden_states(plan["ids"], plan["cu"], plan["pos"], L)
+            vals = vm.values(vh.index_select(0, plan["vsel"]))
+            out_v = torch.zeros((B + 1, T_r), dtype=torch.float32, device=vals.device)
+            mb["vpred"] = out_v.index_put((plan["vr"], plan["vc"]), vals.float())[:B]     # padded entries land in dump row B
         loss, st = t.micro_loss(mb)
         (loss / accum).backward()
         with torch.no_grad():
@@ -107,6 +113,20 @@ class GraphedMicroStep:
         accum = int(getattr(self.t, "_accum_steps", self.t.args.gradient_accumulation_steps))
         key = (T_b, R_b, B, L, accum, tuple(sorted((k, tuple(v.shape), str(v.dtype)) for k, v in tens.items())))
         padded = self._pad_plan(plan, B, pad_id, T_b, R_b)
+        if self.t.uses_value_model:
+            # value positions (columns ctx-1 .. L-2 of every real token, models/qwen2.py response_logprobs), padded to a bucket
+            col, row = plan["col"], plan["row"]
+            vsel = ((col >= ctx - 1) & (col <= L - 2)).nonzero(as_tuple=False).squeeze(1)
+            nv = vsel.numel()
+            V_b = _round_up(max(nv, 1), ROW_BUCKET)
+            dev = vsel.device
+            padded["vsel"] = torch.zeros(V_b, dtype=torch.long, device=dev)
+            padded["vsel"][:nv] = vsel
+            padded["vr"] = torch.full((V_b,), B, dtype=torch.long, device=dev)
+            padded["vr"][:nv] = row[vsel]
+            padded["vc"] = torch.zeros(V_b, dtype=torch.long, device=dev)
+            padded["vc"][:nv] = col[vsel] + 1 - ctx
+            key = key + (V_b,)
         cap = self.graphs.get(key)
         if cap is None:
             n = self.seen.get(key, 0)

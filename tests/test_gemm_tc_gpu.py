@@ -102,6 +102,22 @@ def test_split_k(form, M, N, K, split_k):
     # split order is fixed -> bitwise reproducible
     again = ext.gemm_tc(a, b, a_mn, b_mn, None, None, None, 0, 0.25, None, None, False, 0, 0, split_k)
     assert torch.equal(got, again)
+    # bias rides in the fix-up (small-batch decode projections: few tiles, the weight streamed by all SMs)
+    bias = torch.randn(N, device="cuda").bfloat16()
+    got = ext.gemm_tc(a, b, a_mn, b_mn, None, None, bias, 0, 0.25, None, None, False, 0, 0, split_k)
+    _check(got, 0.25 * want + bias.float(), k=K)
+
+
+def test_small_batch_decode_shapes_take_split_k():
+    """M = 64 rows against 7B-sized weights (4608 / 3584 outputs): automatic dispatch == explicit single-pass kernel."""
+    ext = _ext()
+    for (M, N, K, with_bias) in ((64, 4608, 3584, True), (64, 3584, 18944, False), (256, 3584, 3584, False), (40, 1536, 8960, False)):
+        a, b, want = _operands(M, N, K, False, False, seed=5)
+        bias = torch.randn(N, device="cuda").bfloat16() if with_bias else None
+        auto = ext.gemm_tc(a, b, False, False, None, None, bias)
+        one = ext.gemm_tc(a, b, False, False, None, None, bias, 0, 1.0, None, None, False, 0, 0, 0)
+        _check(auto, want + (bias.float() if with_bias else 0), k=K)
+        _check(one, want + (bias.float() if with_bias else 0), k=K)
 
 
 @pytest.mark.parametrize("cg,bn", [(1, 128), (1, 256), (2, 128), (2, 256), (0, 0)])

@@ -188,13 +188,18 @@ def test_adamw_flat(state_dtype):
     assert _rel(p, p2) < 1e-2 and _rel(m, m2) < 2e-2 and _rel(v, v2) < 2e-2
 
 
-def test_sampling_greedy_and_distribution():
+@pytest.mark.parametrize("impl", [1, 2])
+def test_sampling_greedy_and_distribution(impl):
+    """impl 1: the streaming kernel (one CTA per row, passes through L2); impl 2: the cluster kernel (row resident in the shared
+    memory of 1 / 2 / 4 CTAs, partial results exchanged through distributed shared memory)."""
     n = _native()
     torch.manual_seed(0)
     V = 151936
     logits = torch.randn(64, V, device="cuda").bfloat16()
     tok = n.sample(logits, 0.0, 1.0, 1, 0)
     assert torch.equal(tok.long(), logits.float().argmax(-1))
+    _sample = n.sample
+    n = type("N", (), {"sample": staticmethod(lambda lg, *a: _sample(lg.bfloat16() if impl == 2 else lg, *a, impl=impl))})
     # peaked distribution over few tokens: empirical frequencies match the truncated softmax
     V2 = 1024
     base = torch.full((V2,), -20.0, device="cuda")
@@ -205,7 +210,7 @@ def test_sampling_greedy_and_distribution():
     tok2 = n.sample(lg, 0.9, 0.95, 1234, 7)
     assert torch.equal(tok, tok2)                      # seed-reproducible
     assert not torch.equal(tok, n.sample(lg, 0.9, 0.95, 1235, 7))
-    probs = torch.softmax(base / 0.9, -1)
+    probs = torch.softmax((base.bfloat16().float() if impl == 2 else base) / 0.9, -1)
     sp, si = probs.sort(descending=True)
     keep = (sp.cumsum(0) - sp) < 0.95
     tp = torch.zeros_like(probs)
@@ -234,6 +239,29 @@ def test_sampling_greedy_and_distribution():
     mass_got = torch.zeros(41, device="cuda").index_add_(0, octave, freqw)
     assert (mass_got - mass_want).abs().max().item() < 0.02, (mass_got - mass_want).abs().max().item()
     assert freqw[tpw == 0].sum().item() < 0.02                       # (almost) nothing outside the nucleus
+    if impl == 2:
+        # a 4-CTA cluster (vocabulary too large for two slices) and top_p = 1 (no histogram passes): frequencies of a peaked row
+        Vb = 200_000
+        zb = torch.full((Vb,), -30.0, device="cuda")
+        hot = torch.tensor([5, 49_999, 50_000, 120_001, 199_999], device="cuda")
+        zb[hot] = torch.tensor([2.0, 1.0, 0.0, 1.5, 0.5], device="cuda")
+        for tp_ in (1.0, 0.9):
+            tokb = _sample(zb.bfloat16()[None].expand(20000, Vb).contiguous(), 1.0, tp_, 5, 0, impl=2)
+            pb = torch.softmax(zb.bfloat16().float(), -1)
+            if tp_ < 1.0:
+                spb, sib = pb.sort(descending=True)
+                kb = (spb.cumsum(0) - spb) < tp_
+                tb = torch.zeros_like(pb)
+                tb[sib[kb]] = spb[kb]
+                pb = tb / tb.sum()
+            fb = torch.bincount(tokb.long(), minlength=Vb).float() / 20000
+            assert (fb - pb).abs().max().item() < 0.02, (tp_, (fb - pb).abs().max().item())
+        # per-row seeds / steps are honoured: rows with equal (row id, step) draw the same token from the same distribution
+        lg2 = torch.randn(8, 151936, device="cuda").bfloat16()[:1].expand(8, 151936).contiguous()
+        rid = torch.tensor([0, 0, 1, 1, 2, 2, 3, 3], device="cuda", dtype=torch.int32)
+        rst = torch.tensor([0, 0, 0, 0, 5, 5, 5, 5], device="cuda", dtype=torch.int32)
+        t8 = _sample(lg2, 0.9, 0.95, 11, 0, rid, rst, impl=2)
+        assert torch.equal(t8[0::2], t8[1::2]) and len(set(t8.tolist())) > 1
 
 
 @pytest.mark.parametrize("Hq,Hkv,splits,max_ctx", [(12, 2, 1, 250), (28, 4, 1, 250), (12, 2, 3, 250), (12, 2, 1, 1700), (28, 4, 4, 8200)])

@@ -61,11 +61,17 @@ def test_algorithm_on_native_backend(name, extra, kw, tmp_path):
     assert os.path.isdir(os.path.join(str(tmp_path), "checkpoint-2"))
 
 
-def test_graphed_micro_step_matches_eager(tmp_path):
-    """CUDA-graph replay of fwd+loss+bwd (trainer/graphed.py) reproduces the eager micro-step: stats and gradients."""
-    from nanorlhf_b200.trainer import GRPOTrainer
+@pytest.mark.parametrize("algo", ["grpo", "ppo"])
+def test_graphed_micro_step_matches_eager(tmp_path, algo):
+    """CUDA-graph replay of fwd+loss+bwd (trainer/graphed.py) reproduces the eager micro-step: stats and gradients
+    (PPO: the critic's forward / backward is part of the same graph)."""
+    from nanorlhf_b200.trainer import GRPOTrainer, PPOTrainer
     from nanorlhf_b200.trainer.graphed import GraphedMicroStep
-    t = _setup(tmp_path, GRPOTrainer, {"grpo_sample_N": 4}, gradient_checkpointing=False, train_cuda_graph="on")
+    if algo == "ppo":
+        t = _setup(tmp_path, PPOTrainer, {"policy_learning_rate": 1e-4, "value_learning_rate": 2e-4}, vf_coef=1.0,
+                   gradient_checkpointing=False, train_cuda_graph="on")
+    else:
+        t = _setup(tmp_path, GRPOTrainer, {"grpo_sample_N": 4}, gradient_checkpointing=False, train_cuda_graph="on")
     assert t._graph_micro_step() is not None
     dev, pad = t.device, t.tokenizer.pad_token_id
     B, ctx, T_r = 2, 12, 24
@@ -78,18 +84,25 @@ def test_graphed_micro_step_matches_eager(tmp_path):
             qr[b, ctx - ql:ctx + rl] = torch.randint(0, 4000, (ql + rl,), generator=gen)
             pm[b, :rl] = False
         f = lambda: torch.randn(B, T_r, generator=gen) * 0.1 - 2.0                                   # noqa: E731
-        return {"query_responses": qr.to(dev), "padding_mask": pm.to(dev), "logprobs": f().to(dev),
-                "ref_logprobs": f().to(dev), "advantages": torch.randn(B, T_r, generator=gen).to(dev),
-                "context_length": ctx}
+        mb = {"query_responses": qr.to(dev), "padding_mask": pm.to(dev), "logprobs": f().to(dev),
+              "ref_logprobs": f().to(dev), "advantages": torch.randn(B, T_r, generator=gen).to(dev),
+              "context_length": ctx}
+        if algo == "ppo":
+            pm1 = pm.clone()
+            for b, rl in enumerate(rlens):
+                pm1[b, :min(rl + 1, T_r)] = False
+            mb.update(padding_mask_p1=pm1.to(dev), values=torch.randn(B, T_r, generator=gen).to(dev),
+                      returns=torch.randn(B, T_r, generator=gen).to(dev))
+        return mb
 
-    params = [p for p in t.policy.parameters() if p.requires_grad]
+    params = [p for p in t.model.parameters() if p.requires_grad]
 
     def run(step, mb):
         t.optimizer.zero_grad()
         vec = step(mb, ctx, pad).clone()
         return vec, torch.cat([p.grad.detach().float().reshape(-1) for p in params]).clone()
 
-    t.policy.train()
+    t.model.train()
     g = GraphedMicroStep(t)
     mb1, mb2 = make_mb([5, 9], [24, 17]), make_mb([7, 8], [20, 20])          # same bucket, different data
     v_eager, g_eager = run(g, mb1)                                           # first sight of the bucket: eager
