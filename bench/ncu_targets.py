@@ -86,11 +86,11 @@ if which in ("all", "decode_fp8"):
     q = torch.randn(S, Hq, D, device=dev, dtype=torch.bfloat16)
     for _ in range(3):
         native.ext().paged_decode_fp8(q, kq, vq, ks, vs, bt, cl, 1 / math.sqrt(D), 1)
-if which in ("all", "sample"):
+if which in ("all", "sample", "sample_stream"):
     logits = torch.randn(1024, 151936, device=dev, dtype=torch.bfloat16)
     rid = torch.arange(1024, device=dev, dtype=torch.int32)
-    for _ in range(3):
-        native.sample(logits, 0.9, 0.95, 1, 0, rid, rid)
+    for _ in range(3):                       # "sample": the cluster / shared-memory kernel; "sample_stream": the streaming fallback
+        native.sample(logits, 0.9, 0.95, 1, 0, rid, rid, impl=1 if which == "sample_stream" else 0)
 if which in ("all", "deberta_tma"):
     from nanorlhf_b200.models.deberta_v3 import build_bucket_lut
     lens = [1660] * 8

@@ -174,7 +174,9 @@ torch::Tensor gemm_tc(const torch::Tensor& a, const torch::Tensor& b, bool a_mn,
     const int bn = N <= 64 ? 64 : 128;
     const int64_t tiles = ((M + 127) / 128) * ((N + bn - 1) / bn), num_kb = (K + 63) / 64;
     const int sms = num_sms();
-    int64_t splits = splitk_req > 0 ? splitk_req : std::min<int64_t>(std::min<int64_t>(sms / std::max<int64_t>(tiles, 1), num_kb / 4), 16);
+    // measured (bench/sampler_bench.py, profiles/skinny_gemm_split_sweep_r2.json): the last CTA's reduction reads `splits` partial tiles, so
+    // beyond ~4 k-ranges the fix-up costs more than the shorter main loop saves, and work items past one wave (148) cost a second wave
+    int64_t splits = splitk_req > 0 ? splitk_req : std::min<int64_t>(std::min<int64_t>(sms / std::max<int64_t>(tiles, 1), num_kb / 4), 4);
     // (any N: the adapter-input gradient dA = t'^T x is [r, K_in] -- 12 or 24 tiles of a 6.6 k-long contraction)
     if (splitk_req > 0 || (tiles * 2 <= sms && splits >= 2)) {
       splits = std::max<int64_t>(1, std::min<int64_t>(splits, num_kb));

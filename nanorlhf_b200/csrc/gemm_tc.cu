@@ -342,7 +342,9 @@ NRL_DEVICE void gemm_tc_body(const CUtensorMap& tmA, const CUtensorMap& tmB, con
       if (SPLIT) {
         // ---- split-K: park the fp32 partial tile, the last CTA of the tile reduces all partials in split order ----
         const long tile_elems = static_cast<long>(BLOCK_M) * BN;
-        float* mine = p.ws + (static_cast<long>(w % splits) * (num_m * num_n) + tile_id) * tile_elems + static_cast<long>(row_in_tile) * BN;
+        // workspace tile layout [BN / 4 column groups][128 rows][4]: a warp's 32 rows of one column group are 512 contiguous
+        // bytes, for the partial stores here and for the reduction's loads below
+        float* mine = p.ws + (static_cast<long>(w % splits) * (num_m * num_n) + tile_id) * tile_elems + row_in_tile * 4;
 #pragma unroll 1
         for (int ch = 0; ch < BN / 32; ++ch) {
           uint32_t v[32];
@@ -355,7 +357,7 @@ NRL_DEVICE void gemm_tc_body(const CUtensorMap& tmA, const CUtensorMap& tmB, con
           }
 #pragma unroll
           for (int j = 0; j < 32; j += 4)
-            __stcg(reinterpret_cast<float4*>(mine + ch * 32 + j),
+            __stcg(reinterpret_cast<float4*>(mine + (ch * 8 + (j >> 2)) * (BLOCK_M * 4)),
                    make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])));
         }
         __threadfence();                                   // this thread's partial is visible device-wide ...
@@ -369,32 +371,44 @@ NRL_DEVICE void gemm_tc_body(const CUtensorMap& tmA, const CUtensorMap& tmB, con
         }
         named_barrier_sync(2, kEpiThreads);
         if (*s_last && row_ok) {
-          const float* base = p.ws + static_cast<long>(tile_id) * tile_elems + static_cast<long>(row_in_tile) * BN;
+          const float* base = p.ws + static_cast<long>(tile_id) * tile_elems + row_in_tile * 4;
           const long split_stride = static_cast<long>(num_m * num_n) * tile_elems;
           __nv_bfloat16* orow = p.out_bf16 + static_cast<long>(row) * p.out_stride + c.n_blk * BN;
 #pragma unroll 1
-          for (int j = 0; j < BN; j += 8) {
-            if (c.n_blk * BN + j >= p.N) break;            // N % 8 == 0
-            float s8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            for (int sp = 0; sp < splits; ++sp) {
-              const float4 x = __ldcg(reinterpret_cast<const float4*>(base + sp * split_stride + j));
-              const float4 y = __ldcg(reinterpret_cast<const float4*>(base + sp * split_stride + j + 4));
-              s8[0] += x.x; s8[1] += x.y; s8[2] += x.z; s8[3] += x.w; s8[4] += y.x; s8[5] += y.y; s8[6] += y.z; s8[7] += y.w;
+          for (int c0 = 0; c0 < BN; c0 += 32) {
+            if (c.n_blk * BN + c0 >= p.N) break;
+            float acc[32];
+#pragma unroll
+            for (int e = 0; e < 32; ++e) acc[e] = 0.f;
+#pragma unroll 1
+            for (int sp = 0; sp < splits; ++sp) {            // fixed order -> deterministic; 8 independent 16-byte loads in flight
+              const float* b = base + sp * split_stride + (c0 >> 2) * (BLOCK_M * 4);
+              float4 x[8];
+#pragma unroll
+              for (int q = 0; q < 8; ++q) x[q] = __ldcg(reinterpret_cast<const float4*>(b + q * (BLOCK_M * 4)));
+#pragma unroll
+              for (int q = 0; q < 8; ++q) { acc[4 * q] += x[q].x; acc[4 * q + 1] += x[q].y; acc[4 * q + 2] += x[q].z; acc[4 * q + 3] += x[q].w; }
             }
 #pragma unroll
-            for (int e = 0; e < 8; ++e) s8[e] *= p.alpha;
-            if (p.bias != nullptr) {
-              const uint4 bv = *reinterpret_cast<const uint4*>(p.bias + c.n_blk * BN + j);      // N % 8 == 0, bias 16-byte aligned
-              const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+            for (int j = 0; j < 32; j += 8) {
+              if (c.n_blk * BN + c0 + j < p.N) {             // N % 8 == 0
+                float s8[8];
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 bf = unpack_bf16x2(bw[e]);
-                s8[2 * e] += bf.x;
-                s8[2 * e + 1] += bf.y;
+                for (int e = 0; e < 8; ++e) s8[e] = acc[j + e] * p.alpha;
+                if (p.bias != nullptr) {
+                  const uint4 bv = *reinterpret_cast<const uint4*>(p.bias + c.n_blk * BN + c0 + j);      // bias 16-byte aligned
+                  const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float2 bf = unpack_bf16x2(bw[e]);
+                    s8[2 * e] += bf.x;
+                    s8[2 * e + 1] += bf.y;
+                  }
+                }
+                *reinterpret_cast<uint4*>(orow + c0 + j) = make_uint4(pack_bf16x2(s8[0], s8[1]), pack_bf16x2(s8[2], s8[3]),
+                                                                      pack_bf16x2(s8[4], s8[5]), pack_bf16x2(s8[6], s8[7]));
               }
             }
-            *reinterpret_cast<uint4*>(orow + j) = make_uint4(pack_bf16x2(s8[0], s8[1]), pack_bf16x2(s8[2], s8[3]),
-                                                             pack_bf16x2(s8[4], s8[5]), pack_bf16x2(s8[6], s8[7]));
           }
         }
         named_barrier_sync(1, kEpiThreads);                // s_last is rewritten by the next work item

@@ -190,8 +190,8 @@ def test_adamw_flat(state_dtype):
 
 @pytest.mark.parametrize("impl", [1, 2])
 def test_sampling_greedy_and_distribution(impl):
-    """impl 1: the streaming kernel (one CTA per row, passes through L2); impl 2: the cluster kernel (row resident in the shared
-    memory of 1 / 2 / 4 CTAs, partial results exchanged through distributed shared memory)."""
+    """impl 1: the streaming histogram kernel (one CTA per row, passes through L2); impl 2: the cluster kernel (row resident in the
+    shared memory of 1 / 2 / 4 CTAs, partial results exchanged through distributed shared memory, nucleus verified per draw)."""
     n = _native()
     torch.manual_seed(0)
     V = 151936
@@ -246,7 +246,7 @@ def test_sampling_greedy_and_distribution(impl):
         hot = torch.tensor([5, 49_999, 50_000, 120_001, 199_999], device="cuda")
         zb[hot] = torch.tensor([2.0, 1.0, 0.0, 1.5, 0.5], device="cuda")
         for tp_ in (1.0, 0.9):
-            tokb = _sample(zb.bfloat16()[None].expand(20000, Vb).contiguous(), 1.0, tp_, 5, 0, impl=2)
+            tokb = _sample(zb.bfloat16()[None].expand(20000, Vb).contiguous(), 1.0, tp_, 5, 0, impl=24)      # 24: four CTAs per row
             pb = torch.softmax(zb.bfloat16().float(), -1)
             if tp_ < 1.0:
                 spb, sib = pb.sort(descending=True)
@@ -262,6 +262,12 @@ def test_sampling_greedy_and_distribution(impl):
         rst = torch.tensor([0, 0, 0, 0, 5, 5, 5, 5], device="cuda", dtype=torch.int32)
         t8 = _sample(lg2, 0.9, 0.95, 11, 0, rid, rst, impl=2)
         assert torch.equal(t8[0::2], t8[1::2]) and len(set(t8.tolist())) > 1
+        assert torch.equal(t8, _sample(lg2, 0.9, 0.95, 11, 0, rid, rst, impl=22))      # explicit 2-CTA cluster == automatic
+        # a nucleus of ONE token (top_p = 0.5 with a 60 % token): every draw must return it, however many redraws that takes
+        z1 = torch.full((151936,), -2.0, device="cuda")
+        z1[777] = 10.35                                   # softmax mass ~0.6 at T = 1
+        t1 = _sample(z1.bfloat16()[None].expand(512, 151936).contiguous(), 1.0, 0.5, 3, 0, impl=2)
+        assert (t1 == 777).all()
 
 
 @pytest.mark.parametrize("Hq,Hkv,splits,max_ctx", [(12, 2, 1, 250), (28, 4, 1, 250), (12, 2, 3, 250), (12, 2, 1, 1700), (28, 4, 4, 8200)])
