@@ -162,6 +162,11 @@ def main():
         for k, v in m.items():
             if k.startswith("time/") and k.endswith("_s") and "wall" not in k:
                 phase[k] = phase.get(k, 0.0) + v
+        if comm.is_main:
+            g = getattr(trainer, "_graphed", None)
+            print(f"[bench] step {u}: rollout {m.get('time/rollout_s', 0):.2f}s reward {m.get('time/reward_s', 0):.2f}s "
+                  f"logprob {m.get('time/logprob_s', 0):.2f}s train {m.get('time/train_s', 0):.2f}s "
+                  f"(micro-steps so far: {getattr(g, 'replays', 0)} graph replays, {getattr(g, 'eager', 0)} eager)", file=sys.stderr, flush=True)
     ev1.record()
     torch.cuda.synchronize()
     t1 = time.perf_counter()
@@ -210,6 +215,11 @@ def main():
             # imbalance of the whole update surfaces at its first optimizer step); max over ranks; not communication
             "straggler_wait_ms_per_step": wait_ms,
             "optimizer_steps_per_update": args.mini_batches,
+            # micro-steps (forward + loss + backward) since start-up: replayed as CUDA graphs vs run eagerly (first sight of a
+            # shape bucket, or everything if capture is disabled / failed)
+            "train_micro_steps": {"graph_replays": getattr(getattr(trainer, "_graphed", None), "replays", 0),
+                                  "eager": getattr(getattr(trainer, "_graphed", None), "eager", 0),
+                                  "capture_failures": getattr(getattr(trainer, "_graphed", None), "capture_failures", 0)},
         }
         print(json.dumps(line), flush=True)
     trainer.heartbeat.close()

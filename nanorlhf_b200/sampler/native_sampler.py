@@ -358,7 +358,7 @@ class NativeSampler:
                 st[k].copy_(v)
             g = torch.cuda.CUDAGraph()
             n0 = native.launches()
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
                 self._decode_step(st, temperature, top_p, seed, eos_id, pad_id, max_tokens)
             self._kernels_per_step = native.launches() - n0
             for k, v in snap.items():

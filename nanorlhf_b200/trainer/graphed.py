@@ -49,6 +49,8 @@ class GraphedMicroStep:
         self.replays = 0
         self.eager = 0
         self.disabled = False
+        self.failed: Dict[tuple, int] = {}
+        self.capture_failures = 0
 
     # ---- the device-only micro-step ---------------------------------------------------------------
     def _body(self, plan, mb, B, T_r, L, accum):
@@ -131,16 +133,21 @@ class GraphedMicroStep:
         if cap is None:
             n = self.seen.get(key, 0)
             self.seen[key] = n + 1
-            if n == 0 or self.disabled or len(self.graphs) >= MAX_GRAPHS:
+            if n == 0 or self.disabled or len(self.graphs) >= MAX_GRAPHS or self.failed.get(key, 0) >= 2:
                 self.eager += 1
                 return self._body(padded, tens, B, T_r, L, accum)    # eager (also the capture warm-up)
             try:
                 cap = self._capture(key, padded, tens, B, T_r, L, accum)
             except Exception as e:  # noqa: BLE001 -- a step that cannot be captured must still train
                 import warnings
-                warnings.warn(f"CUDA-graph capture of the micro-step failed ({type(e).__name__}: {e}); "
-                              "using eager micro-steps from now on")
-                self.disabled = True                  # capture records, it does not execute: .grad is untouched
+                # capture records, it does not execute: .grad is untouched.  A capture can be invalidated by something
+                # transient (another thread's CUDA call), so the bucket gets one more try on its next occurrence; only
+                # repeated failures turn the graphs off for good.
+                self.failed[key] = self.failed.get(key, 0) + 1
+                self.capture_failures += 1
+                self.disabled = self.capture_failures >= 6
+                warnings.warn(f"CUDA-graph capture of the micro-step failed ({type(e).__name__}: {e}); this step runs eagerly"
+                              + ("; graphs are off from now on" if self.disabled else ""))
                 self.eager += 1
                 return self._body(padded, tens, B, T_r, L, accum)
         else:
@@ -165,7 +172,9 @@ class GraphedMicroStep:
         torch.cuda.synchronize()
         before = native.launches()
         cap.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(cap.graph, pool=self.pool):
+        # thread_local: CUDA calls of OTHER threads (checkpoint writer, pinned-memory prefetch) must not invalidate the capture;
+        # the backward's launches from the autograd thread still land in the capturing stream
+        with torch.cuda.graph(cap.graph, pool=self.pool, capture_error_mode="thread_local"):
             cap.out = self._body(cap.plan, cap.mb, B, T_r, L, accum)
         cap.launches = native.launches() - before
         native._count(-cap.launches)                # capture launched nothing; replays add it back
