@@ -32,9 +32,12 @@ TARGETS = [
     ("comm.cu.o", r"allreduce_adam_mc_kernel<float>", "kar_allreduce_adam_nvls_multimem"),
     ("comm.cu.o", r"allreduce_adam_p2p_kernel<float, 8>", "kar_allreduce_adam_p2p_8"),
     ("sampling.cu.o", r"sample_top_p_kernel<__nv_bfloat16>", "sample_top_p"),
+    ("sampling.cu.o", r"sample_top_p_smem_kernel", "sample_top_p_cluster_smem"),
+    ("gemm_tc.cu.o", r"gemm_tc_fp8_cg2_kernel<256, 2>", "gemm_tc_fp8_cg2_swiglu"),
+    ("rope_kv.cu.o", r"rope_kv_write", "rope_kv_write_decode"),
     ("rl_kernels.cu.o", r"policy_loss_kernel", "policy_loss"),
 ]
-KEY = re.compile(r"\b(UTC[A-Z]*MMA|UTCBAR|UTCCP|LDTM|STTM|UTMALDG|UTMASTG|UTMAPF|UBLKCP|SYNCS|HMMA|LDGSTS|LDSM|MULTIMEM|LDGMC|STGMC|REDG?|ATOMG|F2FP|MUFU)|STRONG\.SYS")
+KEY = re.compile(r"\b(UTC[A-Z]*MMA|UTCBAR|UTCCP|LDTM|STTM|UTMALDG|UTMASTG|UTMAPF|UBLKCP|UCGABAR[A-Z_]*|SYNCS|HMMA|LDGSTS|LDSM|MULTIMEM|LDGMC|STGMC|REDG?|ATOMG|F2FP|MUFU)|STRONG\.SYS")
 
 
 def listing(obj):
@@ -80,7 +83,7 @@ for obj, pat, name in TARGETS:
         prev = i
     with open(os.path.join(OUT, name + ".sass"), "w") as f:
         f.write("\n".join(out) + "\n")
-    tags = [k for k in ("UTCHMMA", "UTCQMMA", "UTCBAR", "LDTM", "UTMALDG", "UTMASTG", "HMMA", "LDGSTS") if any(c.startswith(k) for c in counts)]
+    tags = [k for k in ("UTCHMMA", "UTCQMMA", "UTCBAR", "LDTM", "UTMALDG", "UTMASTG", "UBLKCP", "UCGABAR", "HMMA", "LDGSTS") if any(c.startswith(k) for c in counts)]
     mm = "multimem" if re.search(r"MULTIMEM|LDGMC|STGMC|\.MC\b|LDG\.E\..*HPADD|MMEM", "\n".join(instr)) else ""
     index.append(f"{name}: {len(instr)} instr; " + " ".join(f"{t}x{sum(v for c, v in counts.items() if c.startswith(t))}" for t in tags) + (" " + mm if mm else ""))
 with open(os.path.join(OUT, "INDEX.txt"), "w") as f:
