@@ -100,7 +100,19 @@ ext.kv_cache_write_fp8(kk, vv, kq, vq, ks8, vs8, slots, None)
 ext.paged_decode_fp8(qd1, kq, vq, ks8, vs8, table, ctx, 1 / math.sqrt(128), 1)
 ext.paged_decode_fp8(qd1, kq, vq, ks8, vs8, table, ctx, 1 / math.sqrt(128), 2)
 lg = torch.randn(6, 5000, device=dev, dtype=bf)
-native.sample(lg, 0.9, 0.95, 7, 0)
+native.sample(lg, 0.9, 0.95, 7, 0, impl=1)               # streaming histogram kernel
 native.sample(lg, 0.0, 1.0, 7, 0)
+lgw = torch.randn(6, 151936, device=dev, dtype=bf)
+for impl in (21, 22, 24):                                # cluster kernel: 1 / 2 / 4 CTAs per row (bulk loads, DSMEM exchange)
+    native.sample(lg if impl == 21 else lgw, 0.9, 0.95, 7, 0, impl=impl)
+native.sample(lgw, 1.0, 0.5, 7, 0, impl=2)               # many redraws
+# split-K with bias in the fix-up, and the fused decode-step RoPE + KV page write
+ext.gemm_tc(torch.randn(64, 2048, device=dev, dtype=bf), torch.randn(264, 2048, device=dev, dtype=bf), False, False, None, None,
+            torch.randn(264, device=dev, dtype=bf))
+qkv = torch.randn(5, (Hq + 2 * Hkv) * 128, device=dev, dtype=bf)
+cs, sn = ref.rope_cos_sin(torch.arange(5, device=dev), 128, 1e6)
+sl5 = torch.arange(5, device=dev, dtype=torch.int32) * 7
+ext.rope_kv_write(qkv.clone(), cs, sn, kc, vc, None, None, sl5, Hq, Hkv)
+ext.rope_kv_write(qkv.clone(), cs, sn, kq, vq, ks8, vs8, sl5, Hq, Hkv)
 torch.cuda.synchronize()
 print("sanitize smoke ok", native.launches(), "launches")
