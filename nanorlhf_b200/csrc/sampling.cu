@@ -593,9 +593,11 @@ extern "C" cudaError_t nrl_sample(const void* logits, int is_bf16, long row_stri
     // (21 / 22 / 24: the cluster kernel with 1 / 2 / 4 CTAs per row, for benchmarking)
     int impl = impl_req != 0 ? impl_req : env_impl;
     // slices of <= 100 KB let two CTAs share an SM (one row's load overlaps another row's passes: 235 vs 254 us at 1024 x 151 936)
-    int csize = 1;
+    int cmin = 1;
+    while (cmin < kMaxCluster && (static_cast<long>(V) * 2 + cmin - 1) / cmin > kSliceBytesMax) cmin *= 2;
+    int csize = cmin;
     while (csize < kMaxCluster && (static_cast<long>(V) * 2 + csize - 1) / csize > 100 * 1024) csize *= 2;
-    if (impl > 20) { csize = std::max(csize, std::min(impl - 20, kMaxCluster)); impl = 2; }
+    if (impl > 20) { csize = std::max(cmin, std::min(impl - 20, kMaxCluster)); impl = 2; }
     const int slice = ((V + csize - 1) / csize + 7) / 8 * 8;
     const bool smem_ok = is_bf16 && V % 8 == 0 && row_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0 &&
                          static_cast<long>(slice) * 2 <= kSliceBytesMax && top_p >= 0.5f;     // (rejection rate ~ 1 - top_p)

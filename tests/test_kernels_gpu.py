@@ -262,7 +262,7 @@ def test_sampling_greedy_and_distribution(impl):
         rst = torch.tensor([0, 0, 0, 0, 5, 5, 5, 5], device="cuda", dtype=torch.int32)
         t8 = _sample(lg2, 0.9, 0.95, 11, 0, rid, rst, impl=2)
         assert torch.equal(t8[0::2], t8[1::2]) and len(set(t8.tolist())) > 1
-        assert torch.equal(t8, _sample(lg2, 0.9, 0.95, 11, 0, rid, rst, impl=22))      # explicit 2-CTA cluster == automatic
+        assert torch.equal(t8, _sample(lg2, 0.9, 0.95, 11, 0, rid, rst, impl=24))      # explicit 4-CTA cluster == automatic at this vocabulary
         # a nucleus of ONE token (top_p = 0.5 with a 60 % token): every draw must return it, however many redraws that takes
         z1 = torch.full((151936,), -2.0, device="cuda")
         z1[777] = 10.35                                   # softmax mass ~0.6 at T = 1
