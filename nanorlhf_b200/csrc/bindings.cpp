@@ -182,12 +182,19 @@ torch::Tensor gemm_tc(const torch::Tensor& a, const torch::Tensor& b, bool a_mn,
       splits = std::max<int64_t>(1, std::min<int64_t>(splits, num_kb));
       const int64_t per = (num_kb + splits - 1) / splits;
       splits = (num_kb + per - 1) / per;                                 // no empty k-range
+      // Captured CUDA graphs (decode step, training micro-step) hold these addresses: a workspace that is outgrown is
+      // retired, never freed.  (Automatic dispatch needs at most num_sms tiles of 128 x 128 floats = 9.7 MB < the 16 MB minimum.)
       static thread_local torch::Tensor ws, counters;
+      static thread_local std::vector<torch::Tensor> retired;
       const int64_t need = splits * tiles * 128 * bn;
-      if (!ws.defined() || ws.numel() < need || ws.device() != a.device())
+      if (!ws.defined() || ws.numel() < need || ws.device() != a.device()) {
+        if (ws.defined()) retired.push_back(ws);
         ws = torch::empty({std::max<int64_t>(need, 1 << 22)}, a.options().dtype(torch::kFloat32));
-      if (!counters.defined() || counters.numel() < tiles || counters.device() != a.device())
+      }
+      if (!counters.defined() || counters.numel() < tiles || counters.device() != a.device()) {
+        if (counters.defined()) retired.push_back(counters);
         counters = torch::zeros({std::max<int64_t>(tiles, 4096)}, a.options().dtype(torch::kInt32));
+      }
       const auto BF = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
       CUtensorMap maps2[2];
       maps2[0] = a_mn ? nrl::make_tma_2d(a.data_ptr(), a.size(0), a.size(1), a.stride(0) * 2, 64, 64, BF, 2)

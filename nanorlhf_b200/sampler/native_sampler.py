@@ -58,7 +58,6 @@ class NativeSampler:
         self.prefill_token_budget = prefill_token_budget
         self.sync_every = sync_every
         self.use_cuda_graph = use_cuda_graph
-        self.down_split_k = int(__import__("os").environ.get("NANORLHF_DOWN_SPLITK", "0"))
         self.sharded_sync = None                        # parallel.weight_sync.ShardedWeightSync under fused data parallelism
         self.enable_compaction = True                   # drop finished rows at sync points (tests switch it off for A/B)
         self.layers: List[_LayerWeights] = []
@@ -98,10 +97,9 @@ class NativeSampler:
             xq, xs = native.ext().quant_rows_e4m3(x)
             wq, ws = lw.q8[name]
             return native.ext().gemm_tc_fp8(xq, xs, wq, ws, bias, False)          # kind::f8f6f4 on CTA pairs (gemm_tc.cu)
-        # general tcgen05 GEMM (cta_group::2 where it pays).  down_proj at decode batch sizes is 96 tiles of 140 k-blocks on
-        # 148 SMs -- two waves for 1.3 waves of work -- so its contraction is split (in-kernel ordered fix-up, gemm_tc.cu)
-        sk = self.down_split_k if (name == "wdown" and bias is None and x.shape[0] <= 1536) else 0
-        return _gemm.gemm(x, getattr(lw, name), bias=bias, split_k=sk)
+        # general tcgen05 GEMM (cta_group::2 where it pays); with few output tiles (small decode batches: the tail of a rollout,
+        # the 7B configs) the dispatcher splits the contraction so that all SMs stream the weight (gemm_tc.cu split-K)
+        return _gemm.gemm(x, getattr(lw, name), bias=bias)
 
     def quantize_arena(self):
         """fp8 rollout (rollout_dtype="fp8"): e4m3 copies of the merged arena with per-output-channel scales."""
