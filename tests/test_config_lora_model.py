@@ -119,3 +119,32 @@ def test_save_load_pretrained_roundtrip(tmp_path):
     ids = torch.randint(0, 90, (6,))
     cu = torch.tensor([0, 6], dtype=torch.int32)
     assert torch.allclose(m(ids, cu, torch.arange(6), 6), m2(ids, cu, torch.arange(6), 6), atol=1e-6)
+
+
+def test_grouped_lora_projections_equal_independent_ones():
+    """q/k/v (and gate/up) go through ``lora_group_forward``: same outputs and gradients as calling each LoraLinear on its own
+    (on CUDA the group shares its rank-r launches, ops/gemm.py; here the dispatcher's per-projection path is exercised)."""
+    import torch
+    from nanorlhf_b200.models.lora import LoraLinear, lora_group_forward
+    torch.manual_seed(0)
+    mods = [LoraLinear(torch.nn.Linear(32, n, bias=(n != 16)), r=4, alpha=8) for n in (48, 16, 16)]
+    for m in mods:
+        torch.nn.init.normal_(m.lora_B.weight, std=0.1)
+    x = torch.randn(5, 7, 32, requires_grad=True)
+    ys = lora_group_forward(x, mods)
+    sum(y.square().sum() for y in ys).backward()
+    g_group = [x.grad.clone()] + [m.lora_A.weight.grad.clone() for m in mods] + [m.lora_B.weight.grad.clone() for m in mods]
+    x.grad = None
+    for m in mods:
+        m.zero_grad()
+    ys2 = [m(x) for m in mods]
+    sum(y.square().sum() for y in ys2).backward()
+    g_ind = [x.grad] + [m.lora_A.weight.grad for m in mods] + [m.lora_B.weight.grad for m in mods]
+    for a, b in zip(ys, ys2):
+        assert torch.allclose(a, b, atol=1e-6)
+    for a, b in zip(g_group, g_ind):
+        assert torch.allclose(a, b, atol=1e-5)
+    # a plain nn.Linear in the list (no adapter on that projection) falls back to independent calls
+    mixed = [mods[0], torch.nn.Linear(32, 8)]
+    out = lora_group_forward(x, mixed)
+    assert out[1].shape == (5, 7, 8) and torch.allclose(out[0], mods[0](x))
