@@ -12,6 +12,7 @@
 #ifndef NRL_RUNTIME_NO_PYBIND
 #include "runtime.h"
 
+#include <pybind11/numpy.h>
 #include <pybind11/stl.h>
 #endif
 
@@ -196,6 +197,17 @@ class Scheduler {
   // ---- queries ----
   std::vector<int> group_seqs(int gid) const { return groups_.at(gid).seq_ids; }
   std::vector<int> block_table(int sid) const { return seqs_.at(sid).blocks; }
+  // Row-major [sids.size(), width] page table of a whole batch (unused entries = fill) written to `out`: one call per
+  // re-batch instead of a Python loop over sequences.
+  void block_tables_into(const std::vector<int>& sids, int width, int fill, int* out) const {
+    for (size_t r = 0; r < sids.size(); ++r) {
+      const std::vector<int>& b = seqs_.at(sids[r]).blocks;
+      if (static_cast<int>(b.size()) > width) throw std::runtime_error("block_tables: a sequence holds more pages than the table is wide");
+      int* row = out + r * static_cast<size_t>(width);
+      std::copy(b.begin(), b.end(), row);
+      std::fill(row + b.size(), row + width, fill);
+    }
+  }
   int seq_len(int sid) const { return seqs_.at(sid).num_tokens(); }
   int num_shared_pages(int gid) const { return groups_.at(gid).prompt_len / bm_.block_size(); }
   int num_waiting() const { return static_cast<int>(waiting_.size()); }
@@ -283,6 +295,11 @@ void bind_runtime(py::module_& m) {
       .def("finish", &Scheduler::finish)
       .def("group_seqs", &Scheduler::group_seqs)
       .def("block_table", &Scheduler::block_table)
+      .def("block_tables", [](const Scheduler& self, const std::vector<int>& sids, int width, int fill) {
+             py::array_t<int> out({static_cast<py::ssize_t>(sids.size()), static_cast<py::ssize_t>(width)});
+             self.block_tables_into(sids, width, fill, out.mutable_data());
+             return out;
+           }, py::arg("seq_ids"), py::arg("width"), py::arg("fill"))
       .def("seq_len", &Scheduler::seq_len)
       .def("num_shared_pages", &Scheduler::num_shared_pages)
       .def("num_waiting", &Scheduler::num_waiting)

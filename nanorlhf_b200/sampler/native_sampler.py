@@ -433,10 +433,7 @@ class NativeSampler:
                 S = max(128, (S_real + 127) // 128 * 128) if self.use_cuda_graph else S_real
                 st = self._alloc_state(S, per_seq_blocks, max_tokens, pad_id)
                 st["block_tables"].fill_(scratch_block)
-                bt = torch.full((S_real, per_seq_blocks), scratch_block, dtype=torch.int32)
-                for r, sid in enumerate(new_running):
-                    t = sched.block_table(sid)
-                    bt[r, :len(t)] = torch.tensor(t, dtype=torch.int32)
+                bt = torch.from_numpy(sched.block_tables(new_running, per_seq_blocks, scratch_block))     # built by the C++ scheduler
                 st["block_tables"][:S_real].copy_(bt.to(dev))
                 st["row_ids"][:S_real].copy_(torch.tensor(new_running, dtype=torch.int32))
                 nk = len(keep_rows)

@@ -27,6 +27,12 @@ def test_prefix_sharing_and_reserve_policy():
     tables = [s.block_table(i) for i in seqs]
     assert all(t[:2] == tables[0][:2] for t in tables) and len({t[2] for t in tables}) == 4
     assert all(len(t) == 5 for t in tables)        # ceil((40+30)/16) = 5 pages reserved per sample
+    bt = s.block_tables(seqs, 7, -1)               # the whole batch's page table in one call (what the sampler uploads)
+    assert bt.shape == (4, 7) and bt.dtype.name == "int32"
+    assert [row[:5].tolist() for row in bt] == tables and (bt[:, 5:] == -1).all()
+    import pytest
+    with pytest.raises(RuntimeError):
+        s.block_tables(seqs, 3, -1)                # narrower than a sequence's page list
     assert s.num_free_blocks() == 64 - (2 + 4 * 3)
     tok, slot = s.prefill_slots(g)
     assert len(tok) == 32 + 4 * 8 and tok[:32] == list(range(32))
