@@ -125,8 +125,14 @@ def _fix_sqrt(s: str) -> str:
 
 def strip_string(s: str, keep_equation: bool = False) -> str:
     s = str(s).strip()
+    inner = get_boxed(s) if "\\boxed" in s or "\\fbox" in s else None         # \boxed{7} on either side -> 7
+    if inner:
+        s = inner
     s = s.replace("\n", "").replace("\\!", "").replace("\\\\", "\\")
     s = s.replace("tfrac", "frac").replace("dfrac", "frac")
+    s = re.sub(r"\\le(?![a-zA-Z])", r"\\leq", s)
+    s = re.sub(r"\\ge(?![a-zA-Z])", r"\\geq", s)
+    s = s.replace("\\neq", "\\ne")
     s = s.replace("\\left", "").replace("\\right", "")
     s = s.replace("\\{", "{").replace("\\}", "}")
     s = s.replace("^{\\circ}", "").replace("^\\circ", "").replace("°", "")
@@ -189,25 +195,31 @@ def _to_float(s: str) -> Optional[float]:
         return None
 
 
-def numeric_equal(a: float, b: float, rel_tol: float = 1e-4) -> bool:
-    return math.isclose(a, b, rel_tol=rel_tol, abs_tol=1e-9)
+def numeric_equal(a: float, b: float, rel_tol: float = 1e-3, abs_tol: float = 1e-3) -> bool:
+    """The reference's two graders accept a number within rel 1e-3 (latex_answer_check.py:104-121 ``isclose(rel_tol=1e-3)``)
+    OR within abs 1e-3 (eval_utils.py:205 ``isclose(abs_tol=1e-3)``); their results are OR-ed (grpo_r1.py:221)."""
+    return math.isclose(a, b, rel_tol=rel_tol, abs_tol=abs_tol)
 
 
 from ._sym_worker import latex_to_expr_text, symbolic_equal_impl as _symbolic_equal_impl, warm as _warm  # noqa: E402
 
 
 _POOL = None
+_POOL_BROKEN = False          # worker processes cannot start here (e.g. the main module is not importable by "spawn")
 
 
 def _pool():
-    global _POOL
-    if _POOL is None:
+    global _POOL, _POOL_BROKEN
+    if _POOL is None and not _POOL_BROKEN:
         ctx = mp.get_context("spawn")
         _POOL = ctx.Pool(2, maxtasksperchild=500)
         try:                      # pay the interpreter + sympy import once, outside any per-answer timeout
-            _POOL.apply_async(_warm).get(120)
+            _POOL.apply_async(_warm).get(60)
         except Exception:
-            pass
+            import warnings
+            _POOL.terminate()
+            _POOL, _POOL_BROKEN = None, True
+            warnings.warn("rule_math: the sympy worker pool did not start; symbolic checks run on a watchdog thread in this process")
     return _POOL
 
 
@@ -218,11 +230,24 @@ def shutdown_pool():
         _POOL = None
 
 
+def _symbolic_equal_thread(a: str, b: str, timeout_s: float) -> bool:
+    """Fallback without worker processes: a daemon thread that is abandoned (not killed) when it overruns."""
+    import threading
+    box = []
+    t = threading.Thread(target=lambda: box.append(_symbolic_equal_impl(a, b)), daemon=True)
+    t.start()
+    t.join(timeout_s)
+    return bool(box and box[0])
+
+
 def symbolic_equal(a: str, b: str, timeout_s: float = 3.0) -> bool:
     """sympy equivalence in a persistent worker with a real timeout (a hung simplify kills the worker)."""
     global _POOL
+    pool = _pool()
+    if pool is None:
+        return _symbolic_equal_thread(a, b, timeout_s)
     try:
-        return bool(_pool().apply_async(_symbolic_equal_impl, (a, b)).get(timeout_s))
+        return bool(pool.apply_async(_symbolic_equal_impl, (a, b)).get(timeout_s))
     except mp.TimeoutError:
         shutdown_pool()         # the stuck worker is terminated; a fresh pool is built lazily
         return False
@@ -324,12 +349,14 @@ def is_equiv(pred: str, gt: str, use_sympy: bool = True, timeout_s: float = 3.0)
             return True
         return bool(use_sympy and symbolic_equal(f"({la})-({ra})", f"-(({lb})-({rb}))", timeout_s))
     # a numeric ground truth against an answer with words around exactly one number ("5 apples", "x = 5 units")
+    # (the reference's "aggressive" rule, latex_answer_check.py:196-224: only when what is left around the number has no
+    # structure -- no LaTeX command, bracket, comparison or variable -- and a match can only accept, never reject)
     if fb is not None and fa is None:
         nums = _LAST_NUMBER_RE.findall(a)
-        if len(nums) == 1:
+        if len(nums) == 1 and not re.search(r"[\\()\[\]<>,^_=+*/xyz]", a.replace(nums[0], "", 1)):
             f1 = _to_float(_fix_a_slash_b(nums[0].replace(",", "")))
-            if f1 is not None:
-                return numeric_equal(f1, fb)
+            if f1 is not None and numeric_equal(f1, fb):
+                return True
     if use_sympy and len(a) < 200 and len(b) < 200:
         return symbolic_equal(a, b, timeout_s)
     return False

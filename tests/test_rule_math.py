@@ -72,3 +72,19 @@ def test_extract_answer_styles():
     assert rm.extract_answer("The correct option is (C)", dataset="mmlu") == "C"
     assert rm.extract_answer("we get 3 then 4 and finally 19") == "19"
     assert rm.extract_answer("nothing here") is None
+
+
+def test_reference_tolerances_and_notation_forms():
+    """Numeric tolerance = rel 1e-3 OR abs 1e-3 (the union of the reference's two graders, latex_answer_check.py:104-121 and
+    eval_utils.py:205); \\boxed on the ground-truth side, \\le / \\leq, factorials, \\log_b, implicit products after a fraction;
+    the single-number rule accepts only when nothing structured surrounds the number and never rejects on its own."""
+    try:
+        assert rm.iscorrect("12.3456", "12.35") and rm.iscorrect("100.05", "100") and rm.iscorrect("0.0004", "0.0001")
+        assert not rm.iscorrect("1002", "1000") and not rm.iscorrect("12", "12.1")
+        assert rm.iscorrect("7", r"\boxed{7}") and rm.iscorrect(r"x \le 3", r"x \leq 3") and not rm.iscorrect(r"x \leq -5", r"x \geq -5")
+        assert rm.iscorrect(r"2\pi", "6.2832") and rm.iscorrect(r"\sqrt{2}", "1.4142")        # structured answer vs its decimal value
+        assert rm.iscorrect("5!", "120") and rm.iscorrect(r"\log_2 8", "3") and rm.iscorrect(r"\frac{1}{2}x", "x/2")
+        assert not rm.iscorrect(r"\sqrt{5}", "5") and not rm.iscorrect("2x+5", "5") and not rm.iscorrect("5^2", "5")
+        assert rm.iscorrect("x=5 units", "5") and rm.iscorrect("1e3", "1000")
+    finally:
+        rm.shutdown_pool()
