@@ -59,31 +59,85 @@ def extract_answer_is(text: str) -> Optional[str]:
 _LAST_NUMBER_RE = re.compile(r"-?\d[\d,]*(?:\.\d+)?(?:/\d+)?|-?\.\d+")
 
 
+_FEW_SHOT_STOPS = {"math": ("Problem:",), "gsm8k": ("Q: ",), "sat": ("Problem:",), "mmlu": ("Problem:",), "ocw": ("Problem:",),
+                   "gaokao": ("问题 ",), "cmath": ("问题：",), "minif2f": ("Informal:",)}
+
+
 def extract_answer(text: str, dataset: str = "math") -> Optional[str]:
     """Final answer of a free-form solution, in the order the reference's extractors try
-    (/root/reference/examples/r1-v0/utils/data_processing/answer_extraction.py:65-243, re-derived from their behaviour):
-    last ``\\boxed{}`` -> "final answer is $...$" (minerva) -> "the answer is ..." -> ``#### x`` (gsm8k) ->
-    a multiple-choice letter for ``dataset in {"mmlu", "sat", "aqua"}`` -> the last number in the text."""
+    (/root/reference/examples/r1-v0/utils/data_processing/answer_extraction.py:65-338, re-derived from their behaviour):
+    a few-shot continuation is cut at the next exemplar header (``Problem:``, ``Q: ``, ...) -> last ``\\boxed{}`` -> "final
+    answer is $...$" (minerva) -> "the answer is ..." / "答案是" -> ``#### x`` (gsm8k) -> the body of the last ```` ```output ````
+    block (tool-integrated solutions) -> a multiple-choice letter for ``dataset in {"mmlu", "sat", "aqua"}`` -> the last
+    number in the text."""
     if text is None:
         return None
+    for stop in _FEW_SHOT_STOPS.get(dataset, ()):
+        if stop in text:
+            text = text.split(stop, 1)[0]
     b = get_boxed(text)
     if b is not None:
         return b.strip()
+    if dataset in ("mmlu", "sat", "aqua"):
+        m = re.search(r"final answer is \(?([a-eA-E])\)?(?![a-zA-Z])", text)
+        if m:
+            return m.group(1).upper()
     m = re.search(r"[Ff]inal answer is:?\s*\$?(.+?)\$?(?:\.\s*I hope it is correct|\.?\s*$)", text.strip(), re.S)
     if m:
         return m.group(1).strip().strip("$").strip()
     a = extract_answer_is(text)
     if a is not None and a != "":
         return a.split("\n")[0].strip().strip("$").rstrip(".").strip()
+    if "答案是" in text:
+        a = text.split("答案是", 1)[1].strip().split("\n")[0].strip("：:。$ ")
+        if dataset == "cmath":
+            nums = re.findall(r"-?\d+\.?\d*", a)
+            return nums[-1] if nums else None
+        return a or None
     m = re.search(r"####\s*(.+)", text)
     if m:
         return m.group(1).strip().replace(",", "")
+    if "```output" in text:
+        out = text.split("```output")[-1].split("```")[0].strip()
+        if out:
+            return out
     if dataset in ("mmlu", "sat", "aqua"):
         m = re.findall(r"\(?\b([A-E])\b\)?", text)
         if m:
             return m[-1]
     nums = _LAST_NUMBER_RE.findall(text)
     return nums[-1].replace(",", "") if nums else None
+
+
+def extract_answers(question: str, text: str, dataset: str = "math") -> List[str]:
+    """List form (reference ``extract_math_answer``, answer_extraction.py:232-242): every boxed answer of the solution; an
+    answer is split at commas when the question asks for values "separated by commas" (and it is not a tuple / interval) and
+    at ``\\text{ and }``."""
+    for stop in _FEW_SHOT_STOPS.get(dataset, ()):
+        if stop in text:
+            text = text.split(stop, 1)[0]
+    found, rest = [], text
+    while True:
+        idx = max(rest.rfind("\\boxed"), rest.rfind("\\fbox"))
+        if idx < 0:
+            break
+        inner = get_boxed(rest[idx:])
+        if inner is not None:
+            found.append(inner.strip())
+        rest = rest[:idx]
+    found.reverse()
+    if not found:
+        one = extract_answer(text, dataset)
+        found = [one] if one else []
+    out: List[str] = []
+    for ans in found:
+        if "separated by commas" in question and not any(ch in ans for ch in "()[]"):
+            out.extend(a.strip() for a in ans.split(","))
+        elif re.search(r"\\text\{\s*and\s*\}", ans):
+            out.extend(a.strip() for a in re.split(r"\\text\{\s*and\s*\}", ans))
+        else:
+            out.append(ans)
+    return out
 
 
 # --------------------------------------------------------------------------------------------------
@@ -129,7 +183,11 @@ def strip_string(s: str, keep_equation: bool = False) -> str:
     if inner:
         s = inner
     s = s.replace("\n", "").replace("\\!", "").replace("\\\\", "\\")
-    s = s.replace("tfrac", "frac").replace("dfrac", "frac")
+    s = s.replace("tfrac", "frac").replace("dfrac", "frac").replace("cfrac", "frac")
+    s = s.replace("x\\in", "")
+    s = s.replace("infinity", "\\infty")
+    s = re.sub(r"(?<![a-zA-Z\\])inf(?![a-zA-Z])", r"\\infty", s)
+    s = s.replace("+\\infty", "\\infty")
     s = re.sub(r"\\le(?![a-zA-Z])", r"\\leq", s)
     s = re.sub(r"\\ge(?![a-zA-Z])", r"\\geq", s)
     s = s.replace("\\neq", "\\ne")
@@ -151,6 +209,11 @@ def strip_string(s: str, keep_equation: bool = False) -> str:
         s = "0" + s
     if not keep_equation and len(s.split("=")) == 2 and len(s.split("=")[0]) <= 2:
         s = s.split("=")[1]
+    s = re.sub(r"(\d+)\.0+(?=\D|$)", r"\1", s)             # 3.000 -> 3, 2.0x -> 2x
+    if "j" in s and "i" not in s and re.search(r"(?<![a-zA-Z])j(?![a-zA-Z])", s):
+        s = re.sub(r"(?<![a-zA-Z])j(?![a-zA-Z])", "i", s)      # engineering notation of the imaginary unit
+    s = re.sub(r"\{(?:c|m)?m\}(?:\^\{?[23]\}?)?", "", s)        # 5{cm}^2
+    s = re.sub(r"\s*p\.m\.$", "", s)
     s = _fix_sqrt(s)
     s = s.replace(" ", "")
     s = _fix_fracs(s)

@@ -88,3 +88,19 @@ def test_reference_tolerances_and_notation_forms():
         assert rm.iscorrect("x=5 units", "5") and rm.iscorrect("1e3", "1000")
     finally:
         rm.shutdown_pool()
+
+
+def test_extractor_family_and_normaliser_breadth():
+    """The remaining extractor behaviours of answer_extraction.py:65-338: tool output blocks, few-shot truncation, SAT / MMLU
+    letters, the CJK answer marker, the list form; and its normaliser's cfrac / infinity / trailing-zero / imaginary-unit rules."""
+    assert rm.extract_answer("work\n```output\n42\n```\ndone") == "42"
+    assert rm.extract_answer("so the final answer is (B). yes", dataset="sat") == "B"
+    assert rm.extract_answer("计算得 答案是：12。\n", dataset="cmath") == "12"
+    assert rm.extract_answer("答案是 $x+1$\n问题 2", dataset="gaokao") == "x+1"
+    assert rm.extract_answer("The answer is 5.\n\nProblem: next one \\boxed{9}", dataset="math") == "5"      # next exemplar is cut
+    assert rm.extract_answers("Enter all solutions, separated by commas.", r"so \boxed{1, 2,3}") == ["1", "2", "3"]
+    assert rm.extract_answers("q", r"\boxed{x=1 \text{ and } y=2}") == ["x=1", "y=2"]
+    assert rm.extract_answers("q", r"first \boxed{3} then \boxed{(1,2)}") == ["3", "(1,2)"]
+    assert rm.strip_string(r"\cfrac{1}{2}") == r"\frac{1}{2}" and rm.strip_string("3.000") == "3" and rm.strip_string("1+2j") == "1+2i"
+    assert rm.strip_string("(-inf, 3]") == r"(-\infty,3]" and rm.strip_string(r"x\in[1,2]") == "[1,2]" and rm.strip_string("information") == "information"
+    assert rm.iscorrect("3.000", "3") and rm.iscorrect(r"(-\infty, 3]", "(-inf,3]")
