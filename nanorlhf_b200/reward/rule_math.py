@@ -140,6 +140,45 @@ def extract_answers(question: str, text: str, dataset: str = "math") -> List[str
     return out
 
 
+def extract_program(text: str, last_only: bool = True) -> str:
+    """Source of the ```` ```python ```` block(s) of a tool-integrated solution (reference eval_utils.py:14-31): the last
+    block, or all blocks joined, without the fences."""
+    blocks = re.findall(r"```python[^\n]*\n(.*?)(?:\n```|\Z)", text, re.S)
+    if not blocks:
+        return ""
+    return blocks[-1].rstrip() + "\n" if last_only else "\n# ========\n".join(b.rstrip() + "\n" for b in blocks)
+
+
+def ground_truth_of(example: dict, dataset: str) -> Optional[str]:
+    """Normalised ground-truth answer of one benchmark record (reference ``parse_ground_truth``, eval_utils.py:34-78): where
+    each of the evaluation sets keeps its answer."""
+    if "gt" in example:
+        return strip_string(example["gt"])
+    if dataset in ("math", "ocw"):
+        gt = extract_answer(example["solution"])
+    elif dataset == "gsm8k":
+        gt = example["answer"].split("####")[-1]
+    elif dataset in ("gsm-hard", "mawps", "bbh"):
+        gt = example["target"]
+    elif dataset == "svamp":
+        gt = example["Answer"]
+    elif dataset == "asdiv":
+        gt = re.sub(r"\(.*?\)", "", str(example["answer"]))           # "12 (apples)" -> "12"
+    elif dataset == "tabmwp":
+        gt = str(example["answer"])
+        if example.get("ans_type") in ("integer_number", "decimal_number"):
+            if "/" in gt:
+                n, d = gt.split("/")[:2]
+                gt = str(int(n) / int(d))
+            elif "%" in gt:
+                gt = str(float(gt.split("%")[0]) / 100)
+            else:
+                gt = str(float(gt.replace(",", "")))
+    else:
+        raise NotImplementedError(f"ground_truth_of: unknown dataset {dataset!r}")
+    return None if gt is None else strip_string(str(gt).strip())
+
+
 # --------------------------------------------------------------------------------------------------
 # normalisation (MATH "strip_string" family)
 # --------------------------------------------------------------------------------------------------

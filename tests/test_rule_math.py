@@ -104,3 +104,15 @@ def test_extractor_family_and_normaliser_breadth():
     assert rm.strip_string(r"\cfrac{1}{2}") == r"\frac{1}{2}" and rm.strip_string("3.000") == "3" and rm.strip_string("1+2j") == "1+2i"
     assert rm.strip_string("(-inf, 3]") == r"(-\infty,3]" and rm.strip_string(r"x\in[1,2]") == "[1,2]" and rm.strip_string("information") == "information"
     assert rm.iscorrect("3.000", "3") and rm.iscorrect(r"(-\infty, 3]", "(-inf,3]")
+
+
+def test_program_extraction_and_dataset_ground_truths():
+    sol = "first\n```python\nx = 1\nprint(x)\n```\nthen\n```python\ny = 2\nprint(y)\n```\n```output\n2\n```"
+    assert rm.extract_program(sol) == "y = 2\nprint(y)\n"
+    assert rm.extract_program(sol, last_only=False).count("print") == 2 and rm.extract_program("no code") == ""
+    assert rm.ground_truth_of({"solution": r"so \boxed{\dfrac{1}{2}}"}, "math") == r"\frac{1}{2}"
+    assert rm.ground_truth_of({"answer": "work\n#### 1,234"}, "gsm8k") == "1234"
+    assert rm.ground_truth_of({"answer": "12 (apples)"}, "asdiv") == "12"
+    assert rm.ground_truth_of({"answer": "3/4", "ans_type": "decimal_number"}, "tabmwp") == "0.75"
+    assert rm.ground_truth_of({"answer": "25%", "ans_type": "decimal_number"}, "tabmwp") == "0.25"
+    assert rm.ground_truth_of({"target": "7"}, "bbh") == "7" and rm.ground_truth_of({"gt": " 5. "}, "anything") == "5"
