@@ -126,6 +126,8 @@ class RLConfig:
 
     # ---- runtime (B200) --------------------------------------------------------------------
     comm: str = "fused"                         # fused (symmetric-memory kernels) | nccl
+    ddp_bucket_mb: int = 25                     # comm="nccl": gradient buckets all-reduced from backward hooks on the last micro-step
+                                                # of a window (DDP's reducer, 25 MB default); 0 = one all-reduce inside step()
     weight_sync: str = "sharded"                # sharded (K-BC under fused DP: layer-sharded merge + multimem.st into every rank's arena,
                                                 # 7.4 ms at 2 GPUs / 5.8 ms at 8, bit-identical to the local merge) | local (every rank
                                                 # merges its own arena, 13.7 ms); single-GPU runs always merge locally

@@ -102,6 +102,13 @@ class FusedAdamW(torch.optim.Optimizer):
         self._fused = None
         self._step = 0
         self.grad_scale = 1.0            # extra multiplier applied to gradients inside the kernel
+        # comm="nccl" bucketed overlap (enable_bucket_overlap): per flat a list of [lo, hi, params pending, launched]
+        self._buckets: Optional[List[List[list]]] = None
+        self._armed = False
+        self._inflight: list = []                # async work handles of the buckets launched from hooks
+        self._order: List[tuple] = []            # global launch sequence of (flat index, bucket index)
+        self._next = 0
+        self.overlap_launched = 0                # buckets whose all-reduce was issued from a backward hook (statistics)
         grad_alloc = param_alloc = None
         if self.comm_mode == "fused":
             from .fused_allreduce import FusedAllReduceAdam
@@ -124,6 +131,92 @@ class FusedAdamW(torch.optim.Optimizer):
             for f in self.flats:
                 comm.broadcast_(f.param, 0)
 
+    # ---- comm="nccl": DDP-style bucketed all-reduce overlapped with the backward -----------------
+    def enable_bucket_overlap(self, bucket_bytes: int = 25 << 20) -> bool:
+        """What DDP's reducer does for the reference (/root/reference/GRPO/grpo_trainer.py:690): gradients are
+        grouped into ~25 MB buckets in reverse parameter order (the order the backward produces them); on the micro-step the
+        trainer arms with ``arm_overlap()`` a post-accumulate hook per parameter counts its bucket down and the bucket's
+        all-reduce is issued asynchronously the moment it is complete, while the backward of the earlier layers still runs.
+        ``step()`` waits for the handles and reduces whatever was not launched (parameters without a gradient, eager
+        fall-backs).  Buckets are contiguous ranges of the flat gradient buffer, so there is no copy in or out.
+        Only the NCCL / gloo path: K-AR (comm="fused") reduces inside the optimizer kernel; CUDA-graph replays fire no hooks
+        (then nothing is launched early and ``step()`` reduces everything, as before)."""
+        if self.comm_mode != "nccl" or self._buckets is not None:
+            return self._buckets is not None
+        self._buckets = []
+        for fi, f in enumerate(self.flats):
+            esz = f.grad.element_size()
+            buckets, hi, members, nbytes = [], f.numel, [], 0
+            for pi in range(len(f.params) - 1, -1, -1):
+                members.append(pi)
+                nbytes += f.params[pi].numel() * esz
+                if nbytes >= bucket_bytes or pi == 0:
+                    lo = f.offsets[pi]
+                    buckets.append([lo, hi, len(members), False, list(members)])
+                    hi, members, nbytes = lo, [], 0
+            self._buckets.append(buckets)
+            for bi, b in enumerate(buckets):
+                for pi in b[4]:
+                    f.params[pi].register_post_accumulate_grad_hook(self._make_hook(fi, bi))
+        self._order = [(fi, bi) for fi, buckets in enumerate(self._buckets) for bi in range(len(buckets))]
+        self._next = len(self._order)
+        return True
+
+    def _make_hook(self, fi: int, bi: int):
+        def hook(_param):
+            if not self._armed:
+                return
+            b = self._buckets[fi][bi]
+            b[2] -= 1
+            if b[2] == 0:
+                self._launch_ready()
+        return hook
+
+    def _launch_ready(self):
+        """Issue the all-reduces strictly in the global bucket sequence (flat by flat, last parameters first), whatever order
+        the hooks complete in: every rank -- including one whose window had no micro-step at all and reduces everything inside
+        ``step()`` -- then enqueues the same collectives in the same order."""
+        import torch.distributed as dist
+        while self._next < len(self._order):
+            fi, bi = self._order[self._next]
+            b = self._buckets[fi][bi]
+            if b[2] != 0:
+                break
+            f = self.flats[fi]
+            self._inflight.append(dist.all_reduce(f.grad[b[0]:b[1]], op=dist.ReduceOp.SUM, async_op=True))
+            b[3] = True
+            self._next += 1
+            self.overlap_launched += 1
+
+    def arm_overlap(self):
+        """Call right before the LAST micro-step's backward of an accumulation window (earlier micro-steps must not reduce:
+        DDP's ``no_sync``)."""
+        if self._buckets is None:
+            return
+        self._armed = True
+        self._next = 0
+        for buckets in self._buckets:
+            for b in buckets:
+                b[2], b[3] = len(b[4]), False
+
+    def _finish_overlap(self) -> bool:
+        """Wait for the early all-reduces and reduce, in sequence, the buckets that were not launched (parameters without a
+        gradient this step, CUDA-graph replays, a window without micro-steps).  True if the gradients are now reduced."""
+        if self._buckets is None:
+            return False
+        import torch.distributed as dist
+        if not self._armed:                       # nothing armed this window: the whole sequence is reduced here
+            self._next = 0
+        self._armed = False
+        for work in self._inflight:
+            work.wait()
+        self._inflight.clear()
+        for fi, bi in self._order[self._next:]:
+            b = self._buckets[fi][bi]
+            dist.all_reduce(self.flats[fi].grad[b[0]:b[1]], op=dist.ReduceOp.SUM)
+        self._next = len(self._order)
+        return True
+
     # ---- bookkeeping -----------------------------------------------------------------------
     @property
     def flats(self):
@@ -140,10 +233,10 @@ class FusedAdamW(torch.optim.Optimizer):
             return 0, f.padded
         return shard_bounds(f.padded, self.world, self.rank)
 
-    def _clip_factor(self) -> float:
+    def _clip_factor(self, already_reduced: bool = False) -> float:
         """Global-norm clipping needs the norm of the REDUCED gradient before any parameter moves, so the gradients are
         all-reduced first (NCCL) and this step then runs the local update on the already reduced buffers."""
-        if self.world > 1:
+        if self.world > 1 and not already_reduced:
             for f in self.flats:
                 self.comm.all_reduce_(f.grad, "sum")
         norm = float(self.grad_norm()) * self.grad_scale / self.world
@@ -154,8 +247,10 @@ class FusedAdamW(torch.optim.Optimizer):
     def step(self, closure=None):
         self._step += 1
         clip, reduced = 1.0, False
+        if self.comm_mode == "nccl" and self._finish_overlap():
+            reduced = True                       # every bucket was all-reduced (most of them during the backward)
         if self.max_grad_norm is not None and self.max_grad_norm > 0:
-            clip, reduced = self._clip_factor(), self.world > 1
+            clip, reduced = self._clip_factor(already_reduced=reduced), self.world > 1
         for g, f in zip(self.param_groups, self._flats):
             if f is None:
                 continue

@@ -125,6 +125,9 @@ class SparseGRPOTrainer(GRPOTrainer):
                         w = float((~mb["padding_mask"]).sum()) / max(n_tok_total, 1.0)
                     else:
                         w = len(b) / len(mini)
+                    if b is buckets[-1]:
+                        self.optimizer.arm_overlap()      # comm="nccl": bucket all-reduces ride the last backward; a rank without
+                                                          # rows issues the same sequence inside step() (parallel/optimizer.py)
                     (loss * w).backward()
                     with torch.no_grad():
                         m = (~mb["padding_mask"]).float()

@@ -188,8 +188,11 @@ class RLTrainer:
         a = self.args
         sd = torch.bfloat16 if a.optimizer_state_dtype == "bf16" else torch.float32
         mode = a.comm if self.device.type == "cuda" else "nccl"
-        return FusedAdamW(groups, lr=a.learning_rate, betas=(a.adam_beta1, a.adam_beta2), eps=a.adam_epsilon,
-                          weight_decay=a.weight_decay, state_dtype=sd, comm=self.comm, comm_mode=mode)
+        opt = FusedAdamW(groups, lr=a.learning_rate, betas=(a.adam_beta1, a.adam_beta2), eps=a.adam_epsilon,
+                         weight_decay=a.weight_decay, state_dtype=sd, comm=self.comm, comm_mode=mode)
+        if opt.comm_mode == "nccl" and a.ddp_bucket_mb > 0:
+            opt.enable_bucket_overlap(int(a.ddp_bucket_mb) << 20)       # DDP-style: buckets reduce while the backward still runs
+        return opt
 
     def get_train_dataloader(self):
         return self.dataloader
@@ -517,6 +520,9 @@ class RLTrainer:
                         rows[(ep, mi, gi)] = graphed(mb, ctx, pad)
                         keys = graphed.stat_keys
                         continue
+                    if mc_start + a.per_device_train_batch_size >= len(mini):
+                        self.optimizer.arm_overlap()        # last micro-step of the window (comm="nccl": bucketed all-reduce
+                                                            # from backward hooks; earlier micro-steps do not reduce = no_sync)
                     out = response_logprobs(self.policy, mb["query_responses"], ctx, pad, a.temperature,
                                             want_entropy=True,
                                             value_model=self.model.value_model if self.uses_value_model else None)

@@ -38,6 +38,7 @@ def _worker(rank, world, port, tmp, algo):
     both = comm.all_gather_cat(flat[None])
     assert torch.equal(both[0], both[1]), "ranks diverged: gradients were not averaged identically"
     assert t.state.global_step == 2 and t.state.episode == 16
+    assert t.optimizer.comm_mode == "nccl" and t.optimizer.overlap_launched > 0      # bucket all-reduces came from backward hooks
     comm.close()
 
 
@@ -76,3 +77,55 @@ def test_broadcast_module_makes_replicas_identical():
     for p in procs:
         p.join(60)
     assert got[0] == got[1]
+
+
+def _overlap_worker(rank, world, port, q):
+    import os
+    import torch
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    from nanorlhf_b200.parallel.comm import Comm
+    from nanorlhf_b200.parallel.optimizer import FusedAdamW
+    comm = Comm.from_env(torch.device("cpu"))
+
+    def run(overlap: bool):
+        torch.manual_seed(0)
+        m = torch.nn.Sequential(torch.nn.Linear(16, 64), torch.nn.Tanh(), torch.nn.Linear(64, 64), torch.nn.Tanh(), torch.nn.Linear(64, 4))
+        opt = FusedAdamW([{"params": list(m.parameters())}], lr=1e-2, comm=comm, comm_mode="nccl", master_weights=False)
+        if overlap:
+            assert opt.enable_bucket_overlap(bucket_bytes=1024)            # 3 buckets: one per Linear
+            assert len(opt._buckets[0]) >= 3
+        g = torch.Generator().manual_seed(10 + rank)                       # every rank sees different data
+        for _step in range(3):
+            opt.zero_grad()
+            for micro in range(2):                                          # accumulation window of 2
+                x = torch.randn(8, 16, generator=g)
+                if overlap and micro == 1:
+                    opt.arm_overlap()
+                (m(x).square().mean() / 2).backward()
+            opt.step()
+        return torch.cat([p.detach().reshape(-1) for p in m.parameters()]), opt.overlap_launched
+
+    p_plain, n0 = run(False)
+    p_overlap, n1 = run(True)
+    q.put((rank, bool(torch.equal(p_plain, p_overlap)), n0, n1, p_overlap.double().sum().item()))
+    comm.barrier()
+    comm.close()
+
+
+def test_bucketed_overlap_equals_single_allreduce():
+    """comm="nccl": all-reducing ~25 MB buckets from backward hooks on the last micro-step (DDP's reducer, reference
+    GRPO/grpo_trainer.py:690) gives bit-identical parameters to one all-reduce inside step(); every bucket is launched
+    during the backward; earlier micro-steps of the window do not communicate."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29850 + (os.getpid() % 100)
+    procs = [ctx.Process(target=_overlap_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in procs)
+    for p in procs:
+        p.join(60)
+    assert all(same for _r, same, _n0, _n1, _s in res), res
+    assert all(n0 == 0 and n1 >= 9 for _r, _same, n0, n1, _s in res), res         # 3 steps x >= 3 buckets, all from hooks
+    assert res[0][4] == res[1][4]                                                # replicas stay identical
