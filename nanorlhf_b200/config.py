@@ -58,6 +58,8 @@ class RLConfig:
     response_length: int = 1500
     temperature: float = 0.9
     top_p: float = 0.95                         # hard-coded in the reference (grpo_trainer.py:127)
+    logprob_top_p_consistent: bool = False      # experimental: score with the top-p-truncated, renormalised softmax the sampler draws
+                                                # from (the reference samples with top_p but scores with the full softmax); slow path
     stop_token: Optional[str] = "eos"
     stop_token_id: Optional[int] = None
     missing_eos_penalty: Optional[float] = None

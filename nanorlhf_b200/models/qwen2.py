@@ -305,6 +305,10 @@ class Qwen2ForCausalLM(Qwen2PreTrained):
 
     def token_logprobs(self, hidden, targets, temperature=1.0, want_entropy=True):
         """(logp, entropy) of ``targets`` under softmax(lm_head(hidden)/temperature); fused K-LP."""
+        top_p = getattr(self, "logprob_top_p", None)          # set by the trainer for ``logprob_top_p_consistent=True``
+        if top_p is not None and top_p < 1.0:
+            from ..ops import reference as _ref
+            return _ref.lmhead_logprob_top_p(hidden, self.lm_head.weight, targets, temperature, top_p)
         return ops.lmhead_logprob(hidden, self.lm_head.weight, targets, temperature, want_entropy)
 
     def forward(self, input_ids, cu_seqlens, position_ids, max_seqlen=None):

@@ -132,6 +132,34 @@ def lmhead_logprob(hidden: torch.Tensor, weight: torch.Tensor, targets: torch.Te
     return logp, ent, lse
 
 
+def lmhead_logprob_top_p(hidden: torch.Tensor, weight: torch.Tensor, targets: torch.Tensor, temperature: float, top_p: float,
+                         chunk: int = 1024) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Log-probs under the distribution the sampler actually draws from: softmax(z / T) restricted to its top-p nucleus and
+    renormalised -- ``logp[t] = z_y - logsumexp_{v in nucleus(t)} z_v``.  The reference samples with top_p = 0.95 but scores
+    with the full softmax (/root/reference/GRPO/grpo_trainer.py:127 vs :547-549); this is the consistent variant
+    (``logprob_top_p_consistent=True``).  Plain autograd over [chunk, V] logits: an experimental switch, not a fast path.  The
+    nucleus is treated as a constant set; a target outside it (never produced by the sampler) gets the full-softmax value.
+    Returns (logp [T], entropy of the truncated distribution [T])."""
+    inv_t = 1.0 / temperature
+    outs, ents = [], []
+    for s in range(0, hidden.shape[0], chunk):
+        z = (hidden[s:s + chunk] @ weight.t()).float() * inv_t
+        with torch.no_grad():
+            p = torch.softmax(z, -1)
+            sp, si = p.sort(-1, descending=True)
+            keep_sorted = (sp.cumsum(-1) - sp) < top_p                     # torch / vLLM nucleus rule; the top token always stays
+            keep = torch.zeros_like(p, dtype=torch.bool).scatter_(1, si, keep_sorted)
+            tgt = targets[s:s + chunk, None].long()
+            inside = keep.gather(1, tgt).squeeze(1)
+        zk = z.masked_fill(~keep, float("-inf"))
+        lse_k, lse_full = torch.logsumexp(zk, -1), torch.logsumexp(z, -1)
+        zy = z.gather(1, tgt).squeeze(1)
+        outs.append(torch.where(inside, zy - lse_k, zy - lse_full))
+        pk = torch.exp(zk - lse_k[:, None])
+        ents.append(lse_k - (pk * z.masked_fill(~keep, 0.0)).sum(-1))
+    return torch.cat(outs), torch.cat(ents)
+
+
 def lmhead_logprob_backward(hidden: torch.Tensor, weight: torch.Tensor, targets: torch.Tensor,
                             lse: torch.Tensor, grad_logp: torch.Tensor, temperature: float,
                             need_weight_grad: bool, chunk: int = 2048):

@@ -100,6 +100,13 @@ class RLTrainer:
         for m in (policy, ref_policy, value_model):
             if m is not None:
                 disable_dropout_in_model(m)
+        if args.logprob_top_p_consistent and args.top_p < 1.0:
+            # experimental: policy and reference log-probs under the truncated softmax the sampler draws from
+            for m in (policy, ref_policy):
+                lm = getattr(m, "base_model", m)
+                for mod in {id(x): x for x in (m, lm, getattr(lm, "model", None))}.values():
+                    if mod is not None and hasattr(mod, "token_logprobs"):
+                        mod.logprob_top_p = float(args.top_p)
         self.model = PolicyAndValueWrapper(policy, value_model if self.uses_value_model else None)
         self.model.to(self.device)
         ref_policy.eval()
@@ -479,7 +486,7 @@ class RLTrainer:
         """CUDA-graph replay of the micro-step (trainer/graphed.py) when the step is graph-safe."""
         a = self.args
         mode = getattr(a, "train_cuda_graph", "auto")
-        ok = (self.device.type == "cuda" and mode != "off" and a.lora_dropout == 0.0
+        ok = (self.device.type == "cuda" and mode != "off" and a.lora_dropout == 0.0 and not a.logprob_top_p_consistent
               and ops.use_native(torch.empty(0, device=self.device)))
         if mode == "auto":
             ok = ok and not a.gradient_checkpointing           # torch.utils.checkpoint is not captured

@@ -86,3 +86,33 @@ def test_max_grad_norm_clips_the_update():
     assert abs(opt.last_grad_norm - 320.0) < 1e-3
     # Adam's first step is lr * sign(g) whatever the scale; the moments carry the clipped gradient
     assert torch.allclose(opt.flats[0].exp_avg[:1024], torch.full((1024,), 0.1 * 10.0 / 320.0), rtol=1e-4)
+
+
+def test_top_p_consistent_logprobs():
+    """``logprob_top_p_consistent``: log-probs of the top-p-truncated, renormalised softmax (the distribution the sampler draws
+    from) -- equal to the full-softmax value plus -log(nucleus mass) inside the nucleus; gradients flow; top_p -> 1 recovers
+    the plain log-softmax."""
+    import torch
+    from nanorlhf_b200.ops import reference as ref
+    torch.manual_seed(0)
+    T, d, V = 7, 16, 50
+    h = torch.randn(T, d, requires_grad=True)
+    w = torch.randn(V, d) * 0.5
+    z = (h @ w.t()) / 0.9
+    p = torch.softmax(z, -1)
+    sp, si = p.sort(-1, descending=True)
+    keep = torch.zeros_like(p, dtype=torch.bool).scatter_(1, si, (sp.cumsum(-1) - sp) < 0.8)
+    tgt_in = si[:, 0]                                                    # the most probable token is always in the nucleus
+    lp, ent = ref.lmhead_logprob_top_p(h, w, tgt_in, 0.9, 0.8)
+    mass = (p * keep).sum(-1)
+    want = torch.log(p.gather(1, tgt_in[:, None]).squeeze(1)) - torch.log(mass)
+    assert torch.allclose(lp, want, atol=1e-5) and (lp > torch.log_softmax(z, -1).gather(1, tgt_in[:, None]).squeeze(1)).all()
+    pk = (p * keep) / mass[:, None]
+    assert torch.allclose(ent, -(pk * torch.log(pk.clamp_min(1e-30))).sum(-1), atol=1e-4)
+    lp.sum().backward()
+    assert h.grad is not None and torch.isfinite(h.grad).all() and h.grad.abs().sum() > 0
+    tgt_out = si[:, -1]                                                  # least probable token: outside -> full-softmax value
+    lp_out, _ = ref.lmhead_logprob_top_p(h.detach(), w, tgt_out, 0.9, 0.8)
+    assert torch.allclose(lp_out, torch.log_softmax(z.detach(), -1).gather(1, tgt_out[:, None]).squeeze(1), atol=1e-5)
+    lp1, _ = ref.lmhead_logprob_top_p(h.detach(), w, tgt_in, 0.9, 1.0)
+    assert torch.allclose(lp1, torch.log_softmax(z.detach(), -1).gather(1, tgt_in[:, None]).squeeze(1), atol=1e-5)

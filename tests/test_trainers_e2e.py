@@ -130,3 +130,16 @@ def test_train_on_all_samples_keeps_step_count(tmp_path):
     assert t.state.global_step == 2
     assert t.optimizer._step - steps0 == 2 * t.args.num_mini_batches
     assert all(k in m for k in GRPO_KEYS)
+
+
+def test_top_p_consistent_scoring_switch(tmp_path):
+    """``logprob_top_p_consistent=True``: policy and reference log-probs come from the truncated, renormalised softmax the
+    sampler draws from (models/qwen2.py token_logprobs -> ops/reference.py lmhead_logprob_top_p); training still steps."""
+    t = build(GRPOTrainer, tmp_path, {"grpo_sample_N": 4}, logprob_top_p_consistent=True, top_p=0.9)
+    lm = getattr(t.policy, "base_model", t.policy)
+    assert lm.logprob_top_p == 0.9 and getattr(t.ref_policy, "logprob_top_p", None) == 0.9
+    m = t.train()
+    assert t.state.global_step == 2
+    assert all(v == v for v in m.values() if isinstance(v, float))
+    # with the switch the old / new log-probs are >= their full-softmax values, so the recorded KL to the reference stays finite
+    assert abs(m["objective/kl_old"]) < 1e3
